@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — planned frames/sec at 1M-frame batches (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path (pp_plan_batch, then the aggregate
+statistics kernel; for N>1 followed by the NCCL all-reduce of the statistics
+vector — the only collective on the path) over one batch of synthetic frames
+that is already resident in HBM.  Workload at every N: BASELINE.json configs[1],
+1,048,576 independent synthetic frames x 12 cars PER GPU (weak scaling; rank r
+plans frames [r*2^20, (r+1)*2^20) of one global counter-based stream).
+
+Prints ONE JSON line (rank 0).  `value` = frames of all ranks / max-over-ranks
+device time; `e2e` = the same metric through pp_plan_batch_host with pinned HOST
+buffers (H2D + D2H inside the timed region); `roofline` = algorithmic bytes
+(1,520 B/frame) / kernel time against the measured HBM peak, plus
+the FP64-issue view that actually bounds this kernel;
+`cpu_baseline` = the reference's own planner classes (oracle/_ref, kind
+"reference") or the C restatement (kind "port") on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FRAMES_PER_GPU = 1 << 20
+N_CARS = 12
+SEED = 0x5EED
+BYTES_IN = 204 + 36 * N_CARS
+BYTES_OUT = 884
+WORKLOAD = "configs[1]: 1,048,576 independent synthetic frames x 12 cars x 3 lanes per GPU"
+METRIC = "planned frames/sec at 1M-frame batch"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_checker():
+    import checkers  # TEST INFRASTRUCTURE (oracle/): used only as the timed CPU baseline
+    if checkers.available("ref"):
+        return checkers.Checker("ref"), "reference"
+    return checkers.Checker("oracle"), "port"
+
+
+def time_cpu(pp, m, n_frames, passes=1):
+    """Reference CPU implementation of the path on all host threads."""
+    chk, kind = cpu_checker()
+    threads = cpu_threads()
+    frames = pp.synth_frames(m, n_frames, N_CARS, seed=SEED)
+    plans = pp.PlanBatch(n_frames, N_CARS, diag=True, cars=False)
+    best = float("inf")
+    for _ in range(passes):
+        t0 = time.perf_counter()
+        chk.plan_into(frames, plans, threads=threads, want_flags=False)
+        best = min(best, time.perf_counter() - t0)
+    return n_frames / best, best, kind, threads
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU planner, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from __graft_entry__ import load_package
+    pp = load_package()
+    m = pp.Map()
+    n = 1 << 18  # bounded sample of the workload per step
+    total_t, total_f = 0.0, 0
+    kind, threads = None, None
+    for i in range(args.warmup + args.steps):
+        fps, t, kind, threads = time_cpu(pp, m, n)
+        if i >= args.warmup:
+            total_t += t
+            total_f += n
+    value = total_f / total_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total_t / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"first {n} frames of the workload per step"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind,
+                         "sample": f"{n} frames per step, {threads} threads, "
+                                   f"{'reference classes (oracle/_ref)' if kind == 'reference' else 'C restatement'}"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if c[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--variant", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from __graft_entry__ import load_package
+    pp = load_package()
+    pp.set_kernel_variant(args.variant)
+
+    n = args.frames
+    m = pp.Map()
+    frames = pp.synth_frames(m, n, N_CARS, seed=SEED, first_frame=rank * n)
+    df = pp.DeviceFrames(frames)
+    dp = pp.DevicePlans(n, N_CARS, diag=True, cars=False)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        pp.plan_batch(m, df, dp)
+        st = pp.stats_batch(dp)
+        if world > 1:
+            dist.all_reduce(st)  # ncclSum of the int64 statistics vector
+        return st
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    fence()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    k_start = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k_stop = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = pp.launch_count()
+    fence()
+    ev0.record(stream)
+    for i in range(args.steps):
+        k_start[i].record(stream)
+        pp.plan_batch(m, df, dp)
+        k_stop[i].record(stream)
+        st = pp.stats_batch(dp)
+        if world > 1:
+            dist.all_reduce(st)
+    ev1.record(stream)
+    fence()
+    launches = pp.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    total_ms = ev0.elapsed_time(ev1)
+    kern_ms = sum(a.elapsed_time(b) for a, b in zip(k_start, k_stop)) / args.steps
+    t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms = float(t[0]), float(t[1])
+    stats = st.cpu().numpy()
+    value = world * n * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host entry point (pinned host buffers) ----
+    hf = pp.FrameBatch(n, N_CARS)
+    for k, v in frames.arrays().items():
+        pinned = torch.from_numpy(v).pin_memory()
+        setattr(hf, k, pinned.numpy())
+        hf.__dict__.setdefault("_keep", []).append(pinned)
+    hp = pp.PlanBatch(n, N_CARS, diag=True, cars=False)
+    for k in hp.fields:
+        pinned = torch.from_numpy(getattr(hp, k)).pin_memory()
+        setattr(hp, k, pinned.numpy())
+        hp.__dict__.setdefault("_keep", []).append(pinned)
+    pp.plan_batch_host(m, hf, hp)  # warm-up (allocates the staging buffers)
+    fence()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        pp.plan_batch_host(m, hf, hp)
+        checksum = float(np.nansum(hp.n_points[:16]))  # the step's result is on the host
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n / float(te[0])
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = (BYTES_IN + BYTES_OUT) * n
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("plan_kernel_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu": n, "cars_per_frame": N_CARS,
+                       "l2_policy": "inputs+outputs (1.6 GB per step) are larger than the 126 MB L2",
+                       "kernel_variant": args.variant,
+                       "step": "pp_plan_batch + pp_stats_batch" + (" + NCCL all-reduce(stats)" if world > 1 else "")},
+            "e2e": {"value": e2e_value, "unit": "frames/s",
+                    "h2d_bytes_per_step": int(hf.bytes_per_frame() * n),
+                    "d2h_bytes_per_step": int(hp.bytes_per_frame() * n),
+                    "api": "pp_plan_batch_host (pinned host buffers, chunked H2D/plan/D2H pipeline)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "plan_thread_per_frame", "kernel_ms": kern_ms,
+                         "algorithmic_bytes_per_frame": BYTES_IN + BYTES_OUT,
+                         "note": "this kernel is FP64-issue/latency bound, not HBM bound: see DESIGN.md §2"},
+            "clocks": clocks,
+            "stats": {"frames": int(stats[0]), "points": int(stats[1]),
+                      "lane_changes": int(stats[8])},
+        }
+        if not args.no_cpu and world == 1:
+            fps, secs, kind, threads = time_cpu(pp, m, n)
+            line["cpu_baseline"] = {
+                "value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                "sample": f"all {n} frames of the workload, 1 pass, {threads} threads ({secs:.1f} s wall)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,220 @@
+"""B200-native batched highway path planner — Python binding of the C ABI.
+
+The product is ``libpp_b200.so`` (hand-written sm_100a CUDA kernels behind the
+``extern "C"`` entry points of ``include/pp.h``).  This module is a thin ctypes
+wrapper used by the tests and ``bench.py``; PyTorch appears only as the owner of
+device memory / streams and for ``torch.distributed`` plumbing.
+
+There is no CPU planning path here: if the shared library is missing the import
+fails, and if no CUDA device is usable every planning call raises ``PPError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .abi import (Config, FrameBatch, Frames, PlanBatch, Plans, default_config, FLAG, FLAG_NAMES,
+                  NUM_FLAGS, STATS_LEN, PATH_LEN, PREV_KEEP, MAP_STRIDE)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpp_b200.so")
+ROOT = os.path.dirname(_HERE)
+MAP_CSV = os.path.join(ROOT, "data", "highway_map.csv")
+
+# every symbol include/pp.h declares (tests check the library exports them all)
+EXPORTS = [
+    "pp_version", "pp_strerror", "pp_last_cuda_error", "pp_device_count", "pp_config_default",
+    "pp_map_create", "pp_map_create_from_csv", "pp_map_destroy", "pp_map_num_waypoints",
+    "pp_map_table", "pp_plan_batch", "pp_plan_batch_host", "pp_stats_batch",
+    "pp_set_kernel_variant", "pp_launch_count", "pp_distancesq_pt_seg_batch",
+    "pp_init_reference_waypoint_batch", "pp_lane_matching_batch", "pp_get_lane_pos_batch",
+    "pp_spline_batch", "pp_closest_waypoint_batch", "pp_next_waypoint_batch",
+    "pp_get_frenet_batch", "pp_get_xy_batch", "pp_synth_frames",
+]
+
+
+class PPError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python {os.path.join(_HERE, 'build.py')}` "
+            "(there is no fallback implementation)")
+    lib = C.CDLL(LIB_PATH)
+    lib.pp_strerror.restype = C.c_char_p
+    lib.pp_last_cuda_error.restype = C.c_char_p
+    lib.pp_launch_count.restype = C.c_int64
+    return lib
+
+
+lib = _load()
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = lib.pp_strerror(rc).decode()
+        detail = lib.pp_last_cuda_error().decode() if rc == -2 else ""
+        raise PPError(f"{what} failed: {msg} {detail}".strip())
+
+
+def launch_count() -> int:
+    return int(lib.pp_launch_count())
+
+
+def device_count() -> int:
+    return int(lib.pp_device_count())
+
+
+def set_kernel_variant(v: int):
+    _check(lib.pp_set_kernel_variant(C.c_int(v)), "pp_set_kernel_variant")
+
+
+def _ptr(t):
+    """Raw address of a torch tensor / numpy array / None."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+class Map:
+    """Owner of a pp_map (host table + device copy on the current CUDA device)."""
+
+    def __init__(self, csv_path: str = MAP_CSV, points=None):
+        self._h = C.c_void_p()
+        if points is not None:
+            wx = np.ascontiguousarray(points[0], dtype=np.float64)
+            wy = np.ascontiguousarray(points[1], dtype=np.float64)
+            rc = lib.pp_map_create(C.c_void_p(wx.ctypes.data), C.c_void_p(wy.ctypes.data),
+                                   C.c_int(len(wx)), C.byref(self._h))
+        else:
+            rc = lib.pp_map_create_from_csv(csv_path.encode(), C.byref(self._h))
+        _check(rc, "pp_map_create")
+        self.n = int(lib.pp_map_num_waypoints(self._h))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def table(self) -> np.ndarray:
+        out = np.zeros((self.n, MAP_STRIDE))
+        _check(lib.pp_map_table(self._h, C.c_void_p(out.ctypes.data)), "pp_map_table")
+        return out
+
+    def close(self):
+        if self._h:
+            lib.pp_map_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def synth_frames(m: Map, n: int, n_cars: int = 12, seed: int = 0x5EED, first_frame: int = 0,
+                 rare_permille: int = 20, max_cars: int | None = None,
+                 out: FrameBatch | None = None) -> FrameBatch:
+    """SURVEY §8d synthetic workload (host generator inside the library)."""
+    fb = out if out is not None else FrameBatch(n, max_cars if max_cars is not None else n_cars)
+    s = fb.struct()
+    _check(lib.pp_synth_frames(m.handle, C.c_uint64(seed), C.c_int64(first_frame), C.c_int64(n),
+                               C.c_int32(n_cars), C.c_int32(rare_permille), C.byref(s)),
+           "pp_synth_frames")
+    return fb
+
+
+def plan_batch_host(m: Map, frames: FrameBatch, plans: PlanBatch | None = None,
+                    cfg: Config | None = None, diag: bool = True, cars: bool = True) -> PlanBatch:
+    """pp_plan_batch_host: host buffers in, host buffers out (copies inside)."""
+    cfg = cfg or default_config()
+    plans = plans or PlanBatch(frames.n, frames.max_cars, diag=diag, cars=cars)
+    fs, ps = frames.struct(), plans.struct()
+    _check(lib.pp_plan_batch_host(m.handle, C.byref(cfg), C.byref(fs), C.byref(ps),
+                                  C.c_int64(frames.n)), "pp_plan_batch_host")
+    return plans
+
+
+class DeviceFrames:
+    """Frames resident in HBM (torch tensors), layout of pp_frames."""
+
+    def __init__(self, frames: FrameBatch, device="cuda"):
+        import torch
+        self.n, self.max_cars = frames.n, frames.max_cars
+        self.t = {k: torch.from_numpy(v).to(device) for k, v in frames.arrays().items()}
+
+    def struct(self) -> Frames:
+        s = Frames()
+        for k, v in self.t.items():
+            setattr(s, k, v.data_ptr())
+        s.max_cars = self.max_cars
+        return s
+
+    def nbytes(self) -> int:
+        return sum(v.numel() * v.element_size() for v in self.t.values())
+
+
+class DevicePlans:
+    """Plans resident in HBM (torch tensors), layout of pp_plans."""
+
+    def __init__(self, n: int, max_cars: int, device="cuda", diag: bool = True, cars: bool = False):
+        import torch
+        self.n, self.max_cars = n, max_cars
+        fields = list(abi.PLAN_CORE) + (abi.PLAN_DIAG if diag else []) + \
+            (abi.PLAN_CARS if cars else [])
+        tmap = {np.float64: torch.float64, np.int32: torch.int32, np.uint32: torch.int32}
+        self.t = {}
+        for name, dt, kind in abi.PLAN_FIELDS:
+            if name in fields:
+                shape = (n,) + abi._inner(kind, max_cars)
+                self.t[name] = torch.zeros(shape, dtype=tmap[dt], device=device)
+
+    def struct(self) -> Plans:
+        s = Plans()
+        for name, _, _ in abi.PLAN_FIELDS:
+            setattr(s, name, self.t[name].data_ptr() if name in self.t else None)
+        return s
+
+    def to_host(self) -> PlanBatch:
+        pb = PlanBatch(self.n, self.max_cars, diag="ego_s" in self.t, cars="car_s" in self.t)
+        for name, dt, _ in abi.PLAN_FIELDS:
+            if name in self.t:
+                a = self.t[name].cpu().numpy()
+                setattr(pb, name, a.view(np.uint32) if dt == np.uint32 else a)
+        return pb
+
+    def nbytes(self) -> int:
+        return sum(v.numel() * v.element_size() for v in self.t.values())
+
+
+def plan_batch(m: Map, frames: DeviceFrames, plans: DevicePlans, cfg: Config | None = None,
+               stream=None, n: int | None = None):
+    """pp_plan_batch on device-resident buffers; asynchronous on `stream`
+    (an int cudaStream_t, default: torch's current stream)."""
+    import torch
+    cfg = cfg or default_config()
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    fs, ps = frames.struct(), plans.struct()
+    _check(lib.pp_plan_batch(m.handle, C.byref(cfg), C.byref(fs), C.byref(ps),
+                             C.c_int64(frames.n if n is None else n), C.c_void_p(stream)),
+           "pp_plan_batch")
+
+
+def stats_batch(plans: DevicePlans, stream=None):
+    """pp_stats_batch -> int64[STATS_LEN] torch tensor on the device."""
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    out = torch.zeros(STATS_LEN, dtype=torch.int64, device=next(iter(plans.t.values())).device)
+    ps = plans.struct()
+    _check(lib.pp_stats_batch(C.byref(ps), C.c_int64(plans.n), C.c_void_p(out.data_ptr()),
+                              C.c_void_p(stream)), "pp_stats_batch")
+    return out

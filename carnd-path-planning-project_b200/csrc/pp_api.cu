@@ -1,0 +1,350 @@
+// pp_api.cu — the extern "C" boundary around the kernels: errors, config,
+// map lifetime, and the host-buffer entry point (H2D / plan / D2H pipeline).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "pp_internal.h"
+
+namespace {
+std::mutex g_err_mu;
+std::string g_err = "";
+std::atomic<long long> g_launches{0};
+}  // namespace
+
+namespace ppi {
+
+void set_cuda_error(const char *what, int cuda_err, const char *text) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  char buf[512];
+  std::snprintf(buf, sizeof buf, "%s: CUDA error %d (%s)", what ? what : "?", cuda_err,
+                text ? text : "");
+  g_err = buf;
+}
+
+void count_launch(int n) { g_launches += n; }
+
+int upload_map(pp_map *m) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_cuda_error("cudaGetDevice", (int)e, cudaGetErrorString(e));
+    cudaGetLastError();
+    return PP_E_CUDA;
+  }
+  const size_t bytes = m->table.size() * sizeof(double);
+  e = cudaMalloc(&m->dev_table, bytes);
+  if (e != cudaSuccess) {
+    m->dev_table = nullptr;
+    set_cuda_error("cudaMalloc(map)", (int)e, cudaGetErrorString(e));
+    cudaGetLastError();
+    return PP_E_CUDA;
+  }
+  e = cudaMemcpy(m->dev_table, m->table.data(), bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(m->dev_table);
+    m->dev_table = nullptr;
+    set_cuda_error("cudaMemcpy(map)", (int)e, cudaGetErrorString(e));
+    cudaGetLastError();
+    return PP_E_CUDA;
+  }
+  m->device = dev;
+  return PP_OK;
+}
+
+void free_map_device(pp_map *m) {
+  if (m && m->dev_table) {
+    cudaFree(m->dev_table);
+    m->dev_table = nullptr;
+  }
+}
+
+}  // namespace ppi
+
+extern "C" {
+
+int pp_version(void) { return PP_VERSION; }
+
+const char *pp_strerror(int code) {
+  switch (code) {
+    case PP_OK: return "ok";
+    case PP_E_ARG: return "invalid argument";
+    case PP_E_CUDA: return "CUDA error (see pp_last_cuda_error)";
+    case PP_E_IO: return "map file could not be read";
+    case PP_E_NOMEM: return "out of memory";
+    case PP_E_RANGE: return "size out of range";
+    default: return "unknown error";
+  }
+}
+
+const char *pp_last_cuda_error(void) {
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  copy = g_err;
+  return copy.c_str();
+}
+
+int pp_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    ppi::set_cuda_error("cudaGetDeviceCount", (int)e, cudaGetErrorString(e));
+    cudaGetLastError();
+    return PP_E_CUDA;
+  }
+  return n;
+}
+
+int64_t pp_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int pp_config_default(pp_config *cfg) {
+  if (!cfg) return PP_E_ARG;
+  cfg->relaxed_acc = 5;                    // src/main.cpp:39
+  cfg->min_relaxed_acc_while_braking = 4;  // :40
+  cfg->maximum_acc = 8;                    // :42
+  cfg->max_speed = 22.2;                   // :45
+  cfg->car_length = 4.5;                   // :46
+  cfg->safety_distance = 2;                // :47
+  cfg->keep_distance = 10;                 // :48
+  cfg->keep_distance_leeway = 0.5;         // :49
+  cfg->test_fast_lane_change = 0;          // :30
+  cfg->reserved = 0;
+  return PP_OK;
+}
+
+// The table is always built on the host.  If no CUDA device is usable the map
+// is still returned (so that Map::Init parity and the synthetic generator can
+// be exercised on a CPU-only box) but it has no device table and every
+// planning call on it fails with PP_E_CUDA.
+int pp_map_create(const double *wx, const double *wy, int n, pp_map **out) {
+  if (!out) return PP_E_ARG;
+  *out = nullptr;
+  pp_map *m = new (std::nothrow) pp_map();
+  if (!m) return PP_E_NOMEM;
+  int rc = ppi::build_map_table(wx, wy, n, m->table);
+  if (rc != PP_OK) {
+    delete m;
+    return rc;
+  }
+  m->n = n;
+  ppi::upload_map(m);  // failure is recorded in pp_last_cuda_error(); see above
+  *out = m;
+  return PP_OK;
+}
+
+int pp_map_create_from_csv(const char *path, pp_map **out) {
+  if (!out) return PP_E_ARG;
+  *out = nullptr;
+  std::vector<double> wx, wy;
+  int rc = ppi::read_map_csv(path, wx, wy);
+  if (rc != PP_OK) return rc;
+  return pp_map_create(wx.data(), wy.data(), (int)wx.size(), out);
+}
+
+void pp_map_destroy(pp_map *map) {
+  if (!map) return;
+  ppi::free_map_device(map);
+  delete map;
+}
+
+int pp_map_num_waypoints(const pp_map *map) { return map ? map->n : PP_E_ARG; }
+
+int pp_map_has_device(const pp_map *map) { return map && map->dev_table ? 1 : 0; }
+
+int pp_map_table(const pp_map *map, double *out) {
+  if (!map || !out) return PP_E_ARG;
+  std::memcpy(out, map->table.data(), map->table.size() * sizeof(double));
+  return PP_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// pp_plan_batch_host: the drop-in for a CPU caller.  Frames are cut into
+// chunks; each chunk's inputs go up, are planned, and its plans come back on
+// one of kStreams streams, so the H2D copy of chunk c+1, the kernel of chunk c
+// and the D2H copy of chunk c-1 overlap.  Device staging buffers are kept per
+// thread between calls.
+// ---------------------------------------------------------------------------
+namespace {
+
+constexpr int kStreams = 3;
+constexpr int64_t kChunk = 65536;
+
+struct Field {
+  size_t elem;   // bytes per element
+  size_t inner;  // elements per frame
+};
+
+struct Staging {
+  int device = -1;
+  int max_cars = -1;
+  int64_t cap = 0;
+  cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+  char *in_buf[kStreams] = {nullptr, nullptr, nullptr};
+  char *out_buf[kStreams] = {nullptr, nullptr, nullptr};
+  size_t in_bytes = 0, out_bytes = 0;
+  void release() {
+    for (int i = 0; i < kStreams; i++) {
+      if (in_buf[i]) cudaFree(in_buf[i]);
+      if (out_buf[i]) cudaFree(out_buf[i]);
+      if (streams[i]) cudaStreamDestroy(streams[i]);
+      in_buf[i] = out_buf[i] = nullptr;
+      streams[i] = nullptr;
+    }
+    cap = 0;
+  }
+  ~Staging() { release(); }
+};
+
+thread_local Staging t_stage;
+
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+#define CK(call)                                                    \
+  do {                                                              \
+    cudaError_t e_ = (call);                                        \
+    if (e_ != cudaSuccess) {                                        \
+      ppi::set_cuda_error(#call, (int)e_, cudaGetErrorString(e_));  \
+      cudaGetLastError();                                           \
+      return PP_E_CUDA;                                             \
+    }                                                               \
+  } while (0)
+
+}  // namespace
+
+extern "C" int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const pp_frames *in,
+                                  const pp_plans *out, int64_t n_frames) {
+  if (!map || !cfg || !in || !out || n_frames < 0) return PP_E_ARG;
+  if (!map->dev_table) {
+    ppi::set_cuda_error("pp_plan_batch_host: map has no device table (no usable CUDA device)", 0,
+                        "");
+    return PP_E_CUDA;
+  }
+  if (in->max_cars < 0 || in->max_cars > PP_MAX_CARS) return PP_E_RANGE;
+  if (n_frames == 0) return PP_OK;
+  const size_t mc = (size_t)in->max_cars;
+
+  // field tables: (host pointer, bytes per frame), in struct order
+  struct HIn { const void *p; size_t bpf; };
+  const HIn hin[14] = {
+      {in->ego_x, 8}, {in->ego_y, 8}, {in->ego_yaw_deg, 8}, {in->ego_speed_mph, 8},
+      {in->prev_n, 4}, {in->prev_x, 8 * PP_PREV_KEEP}, {in->prev_y, 8 * PP_PREV_KEEP},
+      {in->target_lane_in, 4}, {in->n_cars, 4}, {in->car_id, 4 * mc}, {in->car_x, 8 * mc},
+      {in->car_y, 8 * mc}, {in->car_vx, 8 * mc}, {in->car_vy, 8 * mc}};
+  struct HOut { void *p; size_t bpf; };
+  const HOut hout[23] = {
+      {out->next_x, 8 * PP_PATH_LEN}, {out->next_y, 8 * PP_PATH_LEN}, {out->n_points, 4},
+      {out->ego_lane, 4}, {out->ref_wp, 4}, {out->target_lane, 4}, {out->flags, 4},
+      {out->ego_s, 8}, {out->ego_d, 8}, {out->ego_vs, 8}, {out->ego_vd, 8}, {out->ego_speed, 8},
+      {out->ego_acc, 8}, {out->target_speed, 8}, {out->target_time, 8}, {out->next_car_id, 4},
+      {out->next_car_in_target_lane, 4}, {out->car_s, 8 * mc}, {out->car_d, 8 * mc},
+      {out->car_vs, 8 * mc}, {out->car_vd, 8 * mc}, {out->car_lane, 4 * mc},
+      {out->car_next_wp, 4 * mc}};
+  for (int i = 0; i < 9; i++)
+    if (!hin[i].p) return PP_E_ARG;
+  if (mc > 0)
+    for (int i = 9; i < 14; i++)
+      if (!hin[i].p) return PP_E_ARG;
+  for (int i = 0; i < 7; i++)
+    if (!hout[i].p) return PP_E_ARG;
+
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  Staging &sg = t_stage;
+  const int64_t chunk = n_frames < kChunk ? n_frames : kChunk;
+  size_t in_bpf = 0, out_bpf = 0;
+  for (int i = 0; i < 14; i++) in_bpf += align256(hin[i].bpf * (size_t)chunk);
+  for (int i = 0; i < 23; i++) out_bpf += align256(hout[i].bpf * (size_t)chunk);
+  if (sg.device != dev || sg.max_cars != in->max_cars || sg.cap < chunk) {
+    sg.release();
+    for (int i = 0; i < kStreams; i++) {
+      CK(cudaStreamCreateWithFlags(&sg.streams[i], cudaStreamNonBlocking));
+      CK(cudaMalloc(&sg.in_buf[i], in_bpf));
+      CK(cudaMalloc(&sg.out_buf[i], out_bpf));
+    }
+    sg.device = dev;
+    sg.max_cars = in->max_cars;
+    sg.cap = chunk;
+    sg.in_bytes = in_bpf;
+    sg.out_bytes = out_bpf;
+  }
+
+  int slot = 0;
+  for (int64_t lo = 0; lo < n_frames; lo += chunk, slot = (slot + 1) % kStreams) {
+    const int64_t cnt = (n_frames - lo) < chunk ? (n_frames - lo) : chunk;
+    cudaStream_t st = sg.streams[slot];
+    // device-side views of this slot's staging buffers
+    const void *din[14];
+    void *dout[23];
+    size_t off = 0;
+    for (int i = 0; i < 14; i++) {
+      din[i] = sg.in_buf[slot] + off;
+      off += align256(hin[i].bpf * (size_t)sg.cap);
+    }
+    off = 0;
+    for (int i = 0; i < 23; i++) {
+      dout[i] = hout[i].p ? (void *)(sg.out_buf[slot] + off) : nullptr;
+      off += align256(hout[i].bpf * (size_t)sg.cap);
+    }
+    for (int i = 0; i < 14; i++) {
+      if (!hin[i].p || hin[i].bpf == 0) continue;
+      CK(cudaMemcpyAsync((void *)din[i], (const char *)hin[i].p + hin[i].bpf * (size_t)lo,
+                         hin[i].bpf * (size_t)cnt, cudaMemcpyHostToDevice, st));
+    }
+    pp_frames fin;
+    fin.ego_x = (const double *)din[0];
+    fin.ego_y = (const double *)din[1];
+    fin.ego_yaw_deg = (const double *)din[2];
+    fin.ego_speed_mph = (const double *)din[3];
+    fin.prev_n = (const int32_t *)din[4];
+    fin.prev_x = (const double *)din[5];
+    fin.prev_y = (const double *)din[6];
+    fin.target_lane_in = (const int32_t *)din[7];
+    fin.n_cars = (const int32_t *)din[8];
+    fin.car_id = (const int32_t *)din[9];
+    fin.car_x = (const double *)din[10];
+    fin.car_y = (const double *)din[11];
+    fin.car_vx = (const double *)din[12];
+    fin.car_vy = (const double *)din[13];
+    fin.max_cars = in->max_cars;
+    fin.reserved = 0;
+    pp_plans fout;
+    fout.next_x = (double *)dout[0];
+    fout.next_y = (double *)dout[1];
+    fout.n_points = (int32_t *)dout[2];
+    fout.ego_lane = (int32_t *)dout[3];
+    fout.ref_wp = (int32_t *)dout[4];
+    fout.target_lane = (int32_t *)dout[5];
+    fout.flags = (uint32_t *)dout[6];
+    fout.ego_s = (double *)dout[7];
+    fout.ego_d = (double *)dout[8];
+    fout.ego_vs = (double *)dout[9];
+    fout.ego_vd = (double *)dout[10];
+    fout.ego_speed = (double *)dout[11];
+    fout.ego_acc = (double *)dout[12];
+    fout.target_speed = (double *)dout[13];
+    fout.target_time = (double *)dout[14];
+    fout.next_car_id = (int32_t *)dout[15];
+    fout.next_car_in_target_lane = (int32_t *)dout[16];
+    fout.car_s = (double *)dout[17];
+    fout.car_d = (double *)dout[18];
+    fout.car_vs = (double *)dout[19];
+    fout.car_vd = (double *)dout[20];
+    fout.car_lane = (int32_t *)dout[21];
+    fout.car_next_wp = (int32_t *)dout[22];
+    int rc = pp_plan_batch(map, cfg, &fin, &fout, cnt, st);
+    if (rc != PP_OK) return rc;
+    for (int i = 0; i < 23; i++) {
+      if (!hout[i].p || hout[i].bpf == 0) continue;
+      CK(cudaMemcpyAsync((char *)hout[i].p + hout[i].bpf * (size_t)lo, dout[i],
+                         hout[i].bpf * (size_t)cnt, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  for (int i = 0; i < kStreams; i++) CK(cudaStreamSynchronize(sg.streams[i]));
+  return PP_OK;
+}

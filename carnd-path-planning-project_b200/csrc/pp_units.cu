@@ -1,0 +1,258 @@
+// pp_units.cu — unit-level entry points: one batch kernel per reference
+// function, each a thin wrapper around the SAME __device__ code the fused
+// kernel runs (pp_device.cuh).  They exist so that every row of the hot-path
+// table can be parity-tested in isolation (tests/test_gpu_units.py) and so
+// that the host façade (include/pp.hpp) can offer the reference's function
+// names on top of GPU execution.
+#include <cuda_runtime.h>
+
+#include "pp_device.cuh"
+#include "pp_internal.h"
+
+namespace {
+
+using namespace ppd;
+
+constexpr int kB = 128;
+
+__global__ void k_pt_seg(const double *px, const double *py, const double *ax, const double *ay,
+                         const double *bx, const double *by, double *d2, double *rnom,
+                         double *rdenom, double *snom, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const SegDist s = pt_seg(px[i], py[i], ax[i], ay[i], bx[i], by[i]);
+  d2[i] = s.d2;
+  rnom[i] = s.rnom;
+  rdenom[i] = s.rdenom;
+  snom[i] = s.snom;
+}
+
+__device__ void stage_map(double *s_map, const double *table, int n_wp) {
+  for (int i = threadIdx.x; i < n_wp * PP_MAP_STRIDE; i += blockDim.x) s_map[i] = table[i];
+  __syncthreads();
+}
+
+__global__ void k_init_reference(const double *table, int n_wp, const double *x, const double *y,
+                                 int32_t *wp, double *ratio, int64_t n) {
+  extern __shared__ double s_map[];
+  stage_map(s_map, table, n_wp);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  MapView m{s_map, n_wp};
+  RefState rs;
+  init_reference(m, x[i], y[i], rs);
+  wp[i] = rs.wp;
+  ratio[i * 3 + 0] = rs.ratio[0];
+  ratio[i * 3 + 1] = rs.ratio[1];
+  ratio[i * 3 + 2] = rs.ratio[2];
+}
+
+__global__ void k_lane_matching(const double *table, int n_wp, const double *rx, const double *ry,
+                                const double *x, const double *y, const double *vx,
+                                const double *vy, int32_t *ok, int32_t *lane, int32_t *next_wp,
+                                double *s, double *d, double *vs, double *vd, int64_t n) {
+  extern __shared__ double s_map[];
+  stage_map(s_map, table, n_wp);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  MapView m{s_map, n_wp};
+  RefState rs;
+  init_reference(m, rx[i], ry[i], rs);
+  const Match mt = lane_match(m, rs, x[i], y[i]);
+  double a = 0, b = 0;
+  if (mt.ok) project_speed(m, vx[i], vy[i], mt.wp, a, b);
+  ok[i] = mt.ok ? 1 : 0;
+  lane[i] = mt.ok ? mt.lane : -1;
+  next_wp[i] = mt.ok ? mt.wp : 0;
+  s[i] = mt.s;
+  d[i] = mt.d;
+  vs[i] = a;
+  vd[i] = b;
+}
+
+__global__ void k_lane_pos(const double *table, int n_wp, const double *rx, const double *ry,
+                           const double *s, const int32_t *lane, double *ox, double *oy,
+                           int32_t *owp, double *odist, int64_t n) {
+  extern __shared__ double s_map[];
+  stage_map(s_map, table, n_wp);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  MapView m{s_map, n_wp};
+  RefState rs;
+  init_reference(m, rx[i], ry[i], rs);
+  double qx, qy, dist;
+  int wp;
+  lane_pos(m, rs, s[i], lane[i], qx, qy, wp, dist);
+  ox[i] = qx;
+  oy[i] = qy;
+  owp[i] = wp;
+  odist[i] = dist;
+}
+
+__global__ void k_spline(const double *kx, const double *ky, int nk, const double *q, int nq,
+                         double *out, int64_t ns) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns) return;
+  Spline sp;
+  sp.n = nk;
+  for (int k = 0; k < nk; k++) {
+    sp.x[k] = kx[i * nk + k];
+    sp.y[k] = ky[i * nk + k];
+  }
+  spline_fit(sp);
+  for (int j = 0; j < nq; j++) out[i * nq + j] = spline_eval(sp, q[i * nq + j]);
+}
+
+__global__ void k_closest_wp(const double *x, const double *y, const double *mx, const double *my,
+                             int nwp, int32_t *out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = closest_waypoint(x[i], y[i], mx, my, nwp);
+}
+__global__ void k_next_wp(const double *x, const double *y, const double *th, const double *mx,
+                          const double *my, int nwp, int32_t *out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = next_waypoint(x[i], y[i], th[i], mx, my, nwp);
+}
+__global__ void k_get_frenet(const double *x, const double *y, const double *th, const double *mx,
+                             const double *my, int nwp, double *os, double *od, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) get_frenet(x[i], y[i], th[i], mx, my, nwp, os[i], od[i]);
+}
+__global__ void k_get_xy(const double *s, const double *d, const double *ms, const double *mx,
+                         const double *my, int nwp, double *ox, double *oy, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) get_xy(s[i], d[i], ms, mx, my, nwp, ox[i], oy[i]);
+}
+
+int finish(const char *what) {
+  ppi::count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ppi::set_cuda_error(what, (int)e, cudaGetErrorString(e));
+    return PP_E_CUDA;
+  }
+  return PP_OK;
+}
+inline int grid_for(int64_t n) { return (int)((n + kB - 1) / kB); }
+inline size_t map_smem(const pp_map *m) { return (size_t)m->n * PP_MAP_STRIDE * sizeof(double); }
+int need_map(const pp_map *m, const char *who) {
+  if (!m) return PP_E_ARG;
+  if (!m->dev_table) {
+    ppi::set_cuda_error(who, 0, "map has no device table (no usable CUDA device)");
+    return PP_E_CUDA;
+  }
+  if (map_smem(m) > 48 * 1024) return PP_E_RANGE;
+  return PP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pp_distancesq_pt_seg_batch(const double *px, const double *py, const double *ax,
+                               const double *ay, const double *bx, const double *by,
+                               double *out_d2, double *out_rnom, double *out_rdenom,
+                               double *out_snom, int64_t n, void *stream) {
+  if (!px || !py || !ax || !ay || !bx || !by || !out_d2 || !out_rnom || !out_rdenom || !out_snom ||
+      n < 0)
+    return PP_E_ARG;
+  if (n == 0) return PP_OK;
+  k_pt_seg<<<grid_for(n), kB, 0, (cudaStream_t)stream>>>(px, py, ax, ay, bx, by, out_d2, out_rnom,
+                                                         out_rdenom, out_snom, n);
+  return finish("k_pt_seg");
+}
+
+int pp_init_reference_waypoint_batch(const pp_map *map, const double *x, const double *y,
+                                     int32_t *out_ref_wp, double *out_ratio, int64_t n,
+                                     void *stream) {
+  int rc = need_map(map, "pp_init_reference_waypoint_batch");
+  if (rc != PP_OK) return rc;
+  if (!x || !y || !out_ref_wp || !out_ratio || n < 0) return PP_E_ARG;
+  if (n == 0) return PP_OK;
+  k_init_reference<<<grid_for(n), kB, map_smem(map), (cudaStream_t)stream>>>(
+      map->dev_table, map->n, x, y, out_ref_wp, out_ratio, n);
+  return finish("k_init_reference");
+}
+
+int pp_lane_matching_batch(const pp_map *map, const double *rx, const double *ry,
+                           const double *x, const double *y, const double *vx, const double *vy,
+                           int32_t *out_ok, int32_t *out_lane, int32_t *out_next_wp,
+                           double *out_s, double *out_d, double *out_vs, double *out_vd, int64_t n,
+                           void *stream) {
+  int rc = need_map(map, "pp_lane_matching_batch");
+  if (rc != PP_OK) return rc;
+  if (!rx || !ry || !x || !y || !vx || !vy || !out_ok || !out_lane || !out_next_wp || !out_s ||
+      !out_d || !out_vs || !out_vd || n < 0)
+    return PP_E_ARG;
+  if (n == 0) return PP_OK;
+  k_lane_matching<<<grid_for(n), kB, map_smem(map), (cudaStream_t)stream>>>(
+      map->dev_table, map->n, rx, ry, x, y, vx, vy, out_ok, out_lane, out_next_wp, out_s, out_d,
+      out_vs, out_vd, n);
+  return finish("k_lane_matching");
+}
+
+int pp_get_lane_pos_batch(const pp_map *map, const double *rx, const double *ry, const double *s,
+                          const int32_t *lane, double *out_x, double *out_y, int32_t *out_wp,
+                          double *out_dist, int64_t n, void *stream) {
+  int rc = need_map(map, "pp_get_lane_pos_batch");
+  if (rc != PP_OK) return rc;
+  if (!rx || !ry || !s || !lane || !out_x || !out_y || !out_wp || !out_dist || n < 0)
+    return PP_E_ARG;
+  if (n == 0) return PP_OK;
+  k_lane_pos<<<grid_for(n), kB, map_smem(map), (cudaStream_t)stream>>>(
+      map->dev_table, map->n, rx, ry, s, lane, out_x, out_y, out_wp, out_dist, n);
+  return finish("k_lane_pos");
+}
+
+int pp_spline_batch(const double *kx, const double *ky, int32_t n_knots, const double *q,
+                    int32_t n_q, double *out, int64_t n_splines, void *stream) {
+  if (!kx || !ky || !q || !out || n_splines < 0 || n_q < 0) return PP_E_ARG;
+  if (n_knots < 3 || n_knots > 15) return PP_E_RANGE;
+  if (n_splines == 0) return PP_OK;
+  k_spline<<<grid_for(n_splines), kB, 0, (cudaStream_t)stream>>>(kx, ky, n_knots, q, n_q, out,
+                                                                 n_splines);
+  return finish("k_spline");
+}
+
+int pp_closest_waypoint_batch(const double *x, const double *y, const double *maps_x,
+                              const double *maps_y, int32_t n_wp, int32_t *out, int64_t n,
+                              void *stream) {
+  if (!x || !y || !maps_x || !maps_y || !out || n < 0 || n_wp < 1) return PP_E_ARG;
+  if (n == 0) return PP_OK;
+  k_closest_wp<<<grid_for(n), kB, 0, (cudaStream_t)stream>>>(x, y, maps_x, maps_y, n_wp, out, n);
+  return finish("k_closest_wp");
+}
+
+int pp_next_waypoint_batch(const double *x, const double *y, const double *theta,
+                           const double *maps_x, const double *maps_y, int32_t n_wp, int32_t *out,
+                           int64_t n, void *stream) {
+  if (!x || !y || !theta || !maps_x || !maps_y || !out || n < 0 || n_wp < 1) return PP_E_ARG;
+  if (n == 0) return PP_OK;
+  k_next_wp<<<grid_for(n), kB, 0, (cudaStream_t)stream>>>(x, y, theta, maps_x, maps_y, n_wp, out,
+                                                          n);
+  return finish("k_next_wp");
+}
+
+int pp_get_frenet_batch(const double *x, const double *y, const double *theta,
+                        const double *maps_x, const double *maps_y, int32_t n_wp, double *out_s,
+                        double *out_d, int64_t n, void *stream) {
+  if (!x || !y || !theta || !maps_x || !maps_y || !out_s || !out_d || n < 0 || n_wp < 2)
+    return PP_E_ARG;
+  if (n == 0) return PP_OK;
+  k_get_frenet<<<grid_for(n), kB, 0, (cudaStream_t)stream>>>(x, y, theta, maps_x, maps_y, n_wp,
+                                                             out_s, out_d, n);
+  return finish("k_get_frenet");
+}
+
+int pp_get_xy_batch(const double *s, const double *d, const double *maps_s, const double *maps_x,
+                    const double *maps_y, int32_t n_wp, double *out_x, double *out_y, int64_t n,
+                    void *stream) {
+  if (!s || !d || !maps_s || !maps_x || !maps_y || !out_x || !out_y || n < 0 || n_wp < 2)
+    return PP_E_ARG;
+  if (n == 0) return PP_OK;
+  k_get_xy<<<grid_for(n), kB, 0, (cudaStream_t)stream>>>(s, d, maps_s, maps_x, maps_y, n_wp, out_x,
+                                                         out_y, n);
+  return finish("k_get_xy");
+}
+
+}  // extern "C"

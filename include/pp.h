@@ -1,0 +1,269 @@
+/* pp.h — C ABI of the B200-native batched highway path planner.
+ *
+ * One call, pp_plan_batch, replaces the planning step that the reference runs
+ * once per telemetry message inside main::onMessage
+ * (reference src/main.cpp:1254-1457): ego state from the 10th reused point,
+ * Map::init_reference_waypoint / lane_matching / project_speed, the
+ * sensor-fusion matching loop, LaneChangePlanner::calculate_target_lane,
+ * LimitSpeed::calculate, SpeedController and TrajectoryBuilder::build
+ * (tk::spline fit + 0.02 s point emission) — for N independent frames at once,
+ * on the GPU, over struct-of-arrays frame buffers.
+ *
+ * The reference has no FFI of its own for this path (the path is inlined in a
+ * lambda whose only interface is the simulator wire message), so every entry
+ * point below cites the reference lines whose behaviour it reproduces.
+ *
+ * Conventions
+ *   - plain C, no exceptions cross this boundary; every function returns
+ *     PP_OK (0) or a negative PP_E_* code; pp_strerror() names it.
+ *   - "dev" pointers are CUDA device pointers on the device that was current
+ *     when the pp_map was created; "host" pointers are ordinary (ideally
+ *     pinned) host memory.  The caller owns every buffer; the library owns
+ *     pp_map.
+ *   - pp_plan_batch is asynchronous on the caller's stream and re-entrant:
+ *     the reference keeps reference_waypoint_id/ratio as mutable state on
+ *     the shared Map (src/main.cpp:132-133); here that state lives in
+ *     registers per frame, so the map is immutable after creation.
+ *   - There is NO CPU planning path in this library.  If the CUDA device or
+ *     kernels are unavailable the calls fail with PP_E_CUDA.
+ */
+#ifndef PP_B200_H
+#define PP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_VERSION 100
+
+/* Fixed sizes of the reference's planning step. */
+#define PP_NUM_LANES 3    /* src/main.cpp:22  NUM_LANES */
+#define PP_PREV_KEEP 10   /* src/main.cpp:1258 prev_trajectory_length */
+#define PP_PATH_LEN 50    /* src/main.cpp:854,1039 result_points.size() < 50 */
+#define PP_MAX_CARS 64    /* largest n_cars per frame this build accepts (BASELINE config 5) */
+
+/* One row of the uploaded map table (doubles per waypoint):
+ * ref.x ref.y c0.x c0.y c1.x c1.y c2.x c2.y nx ny len0 len1 len2
+ * = Map::Waypoint (src/main.cpp:76-82) plus get_lane_length(i, lane)
+ * (src/main.cpp:138-142) precomputed with the same expression. */
+#define PP_MAP_STRIDE 13
+
+/* Error codes. */
+#define PP_OK 0
+#define PP_E_ARG (-1)      /* null pointer / bad size */
+#define PP_E_CUDA (-2)     /* CUDA runtime error (pp_last_cuda_error() has the text) */
+#define PP_E_IO (-3)       /* map file could not be read */
+#define PP_E_NOMEM (-4)
+#define PP_E_RANGE (-5)    /* n_cars > PP_MAX_CARS, n_waypoints out of range, ... */
+
+/* Per-frame flag bits: one bit per print / log site of the reference, so
+ * that anomalies are data and never abort the batch. */
+#define PP_F_EGO_MATCH_FAIL   (1u << 0)  /* src/main.cpp:1304 "can't lane match ego" */
+#define PP_F_CAR_DROPPED      (1u << 1)  /* :1338 car failed lane_matching, erased */
+#define PP_F_COLLISION        (1u << 2)  /* :1077 "detected collision" */
+#define PP_F_BRAKE            (1u << 3)  /* :1109 */
+#define PP_F_MAXBRAKE         (1u << 4)  /* :1101 */
+#define PP_F_ADJUST           (1u << 5)  /* :1131 */
+#define PP_F_KEEP             (1u << 6)  /* :1146 */
+#define PP_F_SPLINE_INPUT_ERR (1u << 7)  /* :837 non-increasing knot x, truncated */
+#define PP_F_FALLBACK         (1u << 8)  /* :848 angle-based generator taken (silent in the reference) */
+#define PP_F_ACC_OVERRIDE     (1u << 9)  /* :964 */
+#define PP_F_CURV_ADJUST      (1u << 10) /* :988 */
+#define PP_F_LANE_SWITCH_NEG  (1u << 11) /* :711 */
+#define PP_F_VETO             (1u << 12) /* :1366 "target lane too far" */
+#define PP_F_ACCT_HIGH        (1u << 13) /* :950 */
+#define PP_F_ACCN_HIGH        (1u << 14) /* :978 */
+#define PP_F_SPLINE_WARNING   (1u << 15) /* :927 */
+#define PP_F_CLOSED_RANGE     (1u << 16) /* :408 condition true for some car */
+#define PP_F_CLOSED_AHEAD     (1u << 17) /* :423 condition true for some car */
+#define PP_F_CLOSED_BEHIND    (1u << 18) /* :439 condition true for some car */
+#define PP_F_TRANSFORM_ERR    (1u << 19) /* :1015 */
+#define PP_F_COLD_START       (1u << 20) /* :1261 fewer than 10 previous points */
+#define PP_NUM_FLAGS 21
+
+typedef struct pp_map pp_map; /* opaque: host table + device copy */
+
+/* Tunables = the reference's globals (src/main.cpp:30,39-49).
+ * pp_config_default() fills in exactly those literals. */
+typedef struct pp_config {
+  double relaxed_acc;                   /* 5    :39 */
+  double min_relaxed_acc_while_braking; /* 4    :40 */
+  double maximum_acc;                   /* 8    :42 */
+  double max_speed;                     /* 22.2 :45 */
+  double car_length;                    /* 4.5  :46 */
+  double safety_distance;               /* 2    :47 */
+  double keep_distance;                 /* 10   :48 */
+  double keep_distance_leeway;          /* 0.5  :49 */
+  int32_t test_fast_lane_change;        /* 0    :30 */
+  int32_t reserved;
+} pp_config;
+
+/* Input frames, struct of arrays, N frames.  Inner arrays are frame-major:
+ * prev_x[f*PP_PREV_KEEP + i], car_x[f*max_cars + j].
+ * Fields mirror the telemetry the reference reads (src/main.cpp:1233-1252,
+ * 1297,1328-1334); the unused wire fields (s, d, end_path_s/d, car s/d) are
+ * not carried.  Car ids within one frame must be distinct; cars may appear in
+ * any order (the reference iterates a std::map<int,Car>, i.e. ascending id,
+ * and only tie-breaks depend on that order — reproduced here by id). */
+typedef struct pp_frames {
+  const double *ego_x;         /* [N] telemetry x  (used when prev_n < 10, :1233) */
+  const double *ego_y;         /* [N] */
+  const double *ego_yaw_deg;   /* [N] degrees; heading fallback only (:587,596,604) */
+  const double *ego_speed_mph; /* [N] used when prev_n < 10 (:1238-1239) */
+  const int32_t *prev_n;       /* [N] previous_path size; only ">= 10" matters (:1261) */
+  const double *prev_x;        /* [N][10] first 10 points of previous_path_x */
+  const double *prev_y;        /* [N][10] */
+  const int32_t *target_lane_in; /* [N] persistent target_lane (:1195,1355) */
+  const int32_t *n_cars;       /* [N] 0..max_cars */
+  const int32_t *car_id;       /* [N][max_cars] */
+  const double *car_x;         /* [N][max_cars] */
+  const double *car_y;
+  const double *car_vx;
+  const double *car_vy;
+  int32_t max_cars;            /* row length of the car arrays, <= PP_MAX_CARS */
+  int32_t reserved;
+} pp_frames;
+
+/* Output plans, struct of arrays.  next_x/next_y entries at and beyond
+ * n_points are set to quiet NaN.  Any pointer in the "diagnostics" and "per-car" groups may
+ * be NULL (that output is then skipped). */
+typedef struct pp_plans {
+  double *next_x;        /* [N][50]  (:1450-1462) */
+  double *next_y;        /* [N][50] */
+  int32_t *n_points;     /* [N] <= 50 (10 kept + <= 40 new; fewer only in the fallback) */
+  int32_t *ego_lane;     /* [N] */
+  int32_t *ref_wp;       /* [N] reference_waypoint_id, un-wrapped, 0..n_wp (:186) */
+  int32_t *target_lane;  /* [N] after planner + veto: the state carried to the next frame */
+  uint32_t *flags;       /* [N] PP_F_* */
+  /* diagnostics */
+  double *ego_s, *ego_d, *ego_vs, *ego_vd;  /* [N] (:1302,1313) */
+  double *ego_speed, *ego_acc;              /* [N] (:1273-1276,1319-1320) */
+  double *target_speed, *target_time;       /* [N] SpeedController after both limits (:1430,1437) */
+  int32_t *next_car_id;                     /* [N] -1 if none (:1383-1400) */
+  int32_t *next_car_in_target_lane;         /* [N] -1 if none (:1402-1411) */
+  /* per-car results of the sensor-fusion matching loop (:1325-1350) */
+  double *car_s, *car_d, *car_vs, *car_vd;  /* [N][max_cars] */
+  int32_t *car_lane;                        /* [N][max_cars]; -1 = dropped */
+  int32_t *car_next_wp;                     /* [N][max_cars] un-wrapped */
+} pp_plans;
+
+/* Aggregate statistics vector (all int64 so that sums are exact and the
+ * 1/2/4/8-GPU all-reduce is bit-identical). */
+#define PP_STAT_FRAMES 0
+#define PP_STAT_POINTS 1                         /* sum of n_points */
+#define PP_STAT_TARGET_LANE0 2                   /* +lane */
+#define PP_STAT_EGO_LANE0 5                      /* +lane */
+#define PP_STAT_LANE_CHANGES 8                   /* target_lane != ego_lane */
+#define PP_STAT_FLAG0 9                          /* +bit, PP_NUM_FLAGS entries */
+#define PP_STAT_XSUM (PP_STAT_FLAG0 + PP_NUM_FLAGS) /* fixed-point checksum of emitted x,y */
+#define PP_STATS_LEN (PP_STAT_XSUM + 1)
+
+int pp_version(void);
+const char *pp_strerror(int code);
+const char *pp_last_cuda_error(void);
+int pp_device_count(void); /* number of CUDA devices, or PP_E_CUDA */
+
+/* Defaults = the literals at src/main.cpp:30,39-49. */
+int pp_config_default(pp_config *cfg);
+
+/* Map::Init (src/main.cpp:89-131) on the host (same libm as the reference, so
+ * the table is bit-identical), then one upload to the current device. */
+int pp_map_create(const double *wx, const double *wy, int n, pp_map **out);
+/* CSV loader with the reference's parsing (x,y as double; columns 3-5 ignored;
+ * src/main.cpp:1171-1191). */
+int pp_map_create_from_csv(const char *path, pp_map **out);
+void pp_map_destroy(pp_map *map);
+int pp_map_num_waypoints(const pp_map *map);
+/* Copy the host table out: n * PP_MAP_STRIDE doubles. */
+int pp_map_table(const pp_map *map, double *out);
+
+/* The hot path.  in/out hold DEVICE pointers.  Asynchronous on `cuda_stream`
+ * (a cudaStream_t, may be NULL for the default stream). */
+int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_frames *in,
+                  const pp_plans *out, int64_t n_frames, void *cuda_stream);
+
+/* Same call with HOST buffers: uploads the inputs, plans, downloads the
+ * outputs (chunked, copies overlapped with compute), returns when the host
+ * buffers are complete.  This is the drop-in for a CPU caller. */
+int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const pp_frames *in,
+                       const pp_plans *out, int64_t n_frames);
+
+/* Aggregate statistics of a planned batch on the device:
+ * stats_dev[PP_STATS_LEN] (int64, overwritten).  The multi-GPU job all-reduces
+ * this vector (ncclSum) — the only collective on the path. */
+int pp_stats_batch(const pp_plans *plans_dev, int64_t n_frames, int64_t *stats_dev,
+                   void *cuda_stream);
+
+/* Kernel selection for pp_plan_batch: 0 = auto, 1 = one thread per frame
+ * (throughput mapping), 2 = one warp per frame (latency mapping). */
+int pp_set_kernel_variant(int variant);
+/* Number of kernel launches issued by this library since load (bench.py's
+ * gpu_launches). */
+int64_t pp_launch_count(void);
+
+/* ---- unit-level entry points (device pointers), one per reference function.
+ * Each runs the same __device__ code the fused kernel uses. ---- */
+
+/* distancesq_pt_seg (src/helpers.h:188-249): out_d2, out_rnom, out_rdenom, out_snom [n]. */
+int pp_distancesq_pt_seg_batch(const double *px, const double *py, const double *ax,
+                               const double *ay, const double *bx, const double *by,
+                               double *out_d2, double *out_rnom, double *out_rdenom,
+                               double *out_snom, int64_t n, void *cuda_stream);
+
+/* Map::init_reference_waypoint (src/main.cpp:143-197) for n points:
+ * out_ref_wp[n], out_ratio[n][3]. */
+int pp_init_reference_waypoint_batch(const pp_map *map, const double *x, const double *y,
+                                     int32_t *out_ref_wp, double *out_ratio, int64_t n,
+                                     void *cuda_stream);
+
+/* Map::lane_matching + project_speed (src/main.cpp:199-275,330-358) for n
+ * objects, each relative to its own reference point (rx, ry):
+ * out_ok, out_lane, out_next_wp [n] ; out_s, out_d, out_vs, out_vd [n]. */
+int pp_lane_matching_batch(const pp_map *map, const double *rx, const double *ry,
+                           const double *x, const double *y, const double *vx,
+                           const double *vy, int32_t *out_ok, int32_t *out_lane,
+                           int32_t *out_next_wp, double *out_s, double *out_d,
+                           double *out_vs, double *out_vd, int64_t n, void *cuda_stream);
+
+/* Map::get_lane_pos (src/main.cpp:277-328) relative to (rx, ry):
+ * out_x, out_y, out_dist [n]; out_wp [n]. */
+int pp_get_lane_pos_batch(const pp_map *map, const double *rx, const double *ry,
+                          const double *s, const int32_t *lane, double *out_x,
+                          double *out_y, int32_t *out_wp, double *out_dist, int64_t n,
+                          void *cuda_stream);
+
+/* tk::spline::set_points + operator() (src/spline.h:284-396): n_splines
+ * splines of n_knots (3..15) knots each, knots[k*n_splines... ] laid out
+ * spline-major: kx[i*n_knots + k]; each evaluated at n_q query points
+ * q[i*n_q + j] -> out[i*n_q + j]. */
+int pp_spline_batch(const double *kx, const double *ky, int32_t n_knots, const double *q,
+                    int32_t n_q, double *out, int64_t n_splines, void *cuda_stream);
+
+/* Udacity starter helpers (src/helpers.h:43-155); never called by the
+ * reference's planner but part of its API surface. maps_* are device arrays
+ * of n_wp entries. */
+int pp_closest_waypoint_batch(const double *x, const double *y, const double *maps_x,
+                              const double *maps_y, int32_t n_wp, int32_t *out, int64_t n,
+                              void *cuda_stream);
+int pp_next_waypoint_batch(const double *x, const double *y, const double *theta,
+                           const double *maps_x, const double *maps_y, int32_t n_wp,
+                           int32_t *out, int64_t n, void *cuda_stream);
+int pp_get_frenet_batch(const double *x, const double *y, const double *theta,
+                        const double *maps_x, const double *maps_y, int32_t n_wp,
+                        double *out_s, double *out_d, int64_t n, void *cuda_stream);
+int pp_get_xy_batch(const double *s, const double *d, const double *maps_s,
+                    const double *maps_x, const double *maps_y, int32_t n_wp, double *out_x,
+                    double *out_y, int64_t n, void *cuda_stream);
+
+/* ---- synthetic workload (host).  Counter-based RNG
+ * keyed by (seed, frame index): any sub-range can be generated on any rank.
+ * `out` holds HOST pointers (const is cast away; caller-owned). ---- */
+int pp_synth_frames(const pp_map *map, uint64_t seed, int64_t first_frame, int64_t n_frames,
+                    int32_t n_cars, int32_t rare_permille, const pp_frames *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PP_B200_H */

@@ -1,0 +1,186 @@
+"""Pins the C restatement (oracle/pp_oracle.c) before anything trusts it:
+  * against the golden vectors produced by the reference's own code
+    (tests/golden/*.npz, made by tests/golden/make_golden.py),
+  * against the lane-centre arrays in the reference's DrawLines.ipynb,
+  * against the seed known-answer values of SURVEY Appendix B,
+  * and, when oracle/_ref/libppref.so is present, live against the reference
+    harness on fresh seeds (incl. the untouched onMessage lambda).
+All comparisons are bit-exact (same libm, same operation order).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, assert_plans_equal, plans_dict
+
+
+def test_oracle_matches_golden_frames(oracle, golden_frames):
+    fb, want, mask = golden_frames
+    got = oracle.plan(fb)
+    assert_plans_equal(plans_dict(got), want, mask, bitwise_traj=True, what="oracle vs golden: ")
+
+
+def test_map_init_matches_drawlines_notebook(oracle):
+    """DrawLines.ipynb holds all 181 reference points and 3x181 lane-centre
+    points printed with %.4f by reference src/main.cpp:1200-1208."""
+    g = json.load(open(os.path.join(GOLDEN, "drawlines_lanes.json")))
+    t = oracle.map_table()
+    assert t.shape[0] == 181
+    assert np.abs(t[:, 0:2] - np.array(g["wpmap"])).max() <= 5.0001e-5
+    for lane in range(3):
+        err = np.abs(t[:, 2 + 2 * lane:4 + 2 * lane] - np.array(g[f"lane{lane}"])).max()
+        assert err <= 5.0001e-5, (lane, err)
+
+
+def test_appendix_b_map_kats(oracle):
+    t = oracle.map_table()
+    assert t[0, 8] == -0.026938559669005456 and t[0, 9] == -0.99963709115006305
+    assert t[0, 2] == 784.55226438455873 and t[0, 3] == 1133.571572143363
+    assert t[0, 6] == 784.36092192279341 and t[0, 7] == 1125.5738607168157
+    assert t[1, 8] == -0.020896837382490391 and t[1, 2] == 815.24635518148364
+    assert t[180, 8] == -0.16626890051393584 and t[180, 3] == 1134.426400317795
+    # perimeter 6945.554 m, segments 15.89 - 93.04 m (lane 0 centre line lengths are close to the ref line)
+    ref = t[:, 0:2]
+    seg = np.linalg.norm(ref - np.roll(ref, 1, axis=0), axis=1)
+    assert abs(seg.sum() - 6945.554) < 0.5 and 15.8 < seg.min() < 16.0 and 93.0 < seg.max() < 93.1
+
+
+def _frame_a(abi):
+    fb = abi.FrameBatch(1, 12)
+    fb.ego_x[0], fb.ego_y[0] = 909.48, 1128.67
+    fb.n_cars[0] = 3
+    for j, c in enumerate([[0, 1000, 1130, 15, 0.1], [1, 950, 1126, 14, 0], [2, 880, 1124.8, 20, 0]]):
+        fb.car_id[0, j] = c[0]
+        fb.car_x[0, j], fb.car_y[0, j], fb.car_vx[0, j], fb.car_vy[0, j] = c[1:]
+    return fb
+
+
+def test_appendix_b_frames(oracle, abi):
+    """cold-start frame A, then frame B reusing A's points 3..12."""
+    fa = _frame_a(abi)
+    a = oracle.plan(fa)
+    assert a.ref_wp[0] == 5 and a.ego_lane[0] == 1 and a.target_lane[0] == 1 and a.n_points[0] == 50
+    assert a.ego_s[0] == 0 and a.ego_d[0] == 6.1660676684929081
+    assert list(a.car_lane[0, :3]) == [2, 2, 2] and list(a.car_next_wp[0, :3]) == [7, 6, 4]
+    assert a.car_s[0, 0] == 89.840954790310718 and a.car_d[0, 0] == 16.03349966410368
+    assert a.car_vs[0, 0] == 14.642193879004951 and a.car_vd[0, 0] == 3.2582446822836855
+    assert a.car_s[0, 2] == -29.514811630934631 and a.car_vd[0, 2] == -0.005952498793892611
+    assert a.target_speed[0] == 22.199999999999999 and a.target_time[0] == 4.4399999999999995
+    assert (a.next_x[0, 0], a.next_y[0, 0]) == (909.48199898938844, 1128.670063572202)
+    assert (a.next_x[0, 10], a.next_y[0, 10]) == (909.61193330424783, 1128.6741956203637)
+    assert (a.next_x[0, 49], a.next_y[0, 49]) == (912.02874432915644, 1128.7500091916932)
+    fb = _frame_a(abi)
+    fb.prev_n[0] = 47
+    fb.prev_x[0], fb.prev_y[0] = a.next_x[0, 3:13], a.next_y[0, 3:13]
+    b = oracle.plan(fb)
+    assert b.ego_speed[0] == 1.2999999999988825 and b.ego_acc[0] == 0.099999999996727706
+    assert b.ref_wp[0] == 5 and b.ego_lane[0] == 1 and b.ego_d[0] == 6.1618973809581528
+    assert b.ego_vs[0] == 1.2996512961894775 and b.ego_vd[0] == -0.03010827643863451
+    assert b.target_time[0] == 4.1800000000002235
+    assert (b.next_x[0, 0], b.next_y[0, 0]) == (909.49998989390042, 1128.6706357215203)
+    assert (b.next_x[0, 49], b.next_y[0, 49]) == (912.3406106400505, 1128.7591544107854)
+
+
+def test_appendix_b_spline_and_segment_kats(oracle):
+    kx = np.array([[-3, -1, 0, 2, 5, 9.0]])
+    ky = np.array([[0.5, 0.1, 0, -0.2, 0.4, 1.5]])
+    out = oracle.spline(kx, ky, np.array([[-4, 0.5, 4, 10.0]]))[0]
+    assert list(out) == [0.73810308307837136, -0.062533463756177937, 0.11692947360163186,
+                         1.7677983054836433]
+    d2, rnom, rdenom, snom = oracle.distancesq_pt_seg([1, -0.2, -1], [2, 2, 2], [0] * 3, [0] * 3,
+                                                      [4] * 3, [0] * 3)
+    assert list(d2) == [4, 4, 5] and list(rdenom) == [16, 16, 16]
+    assert rnom[0] == 4 and rnom[1] == -0.8 and rnom[2] == 0 and snom[0] == -8
+
+
+def test_oracle_units_match_golden(oracle, golden_units):
+    g = golden_units
+    assert np.array_equal(np.stack(oracle.distancesq_pt_seg(*g["seg_in"])), g["seg_out"])
+    px, py = g["ref_in"]
+    wp, ratio = oracle.init_reference_waypoint(px, py)
+    assert np.array_equal(wp, g["ref_wp"]) and np.array_equal(ratio, g["ref_ratio"])
+    lm = oracle.lane_matching(*g["lm_in"])
+    for k, v in lm.items():
+        assert np.array_equal(v, g["lm_" + k]), k
+    assert (g["lm_ok"] == 0).sum() >= 8  # the far objects really fail
+    lx, ly, lwp, ld = oracle.get_lane_pos(px, py, g["lp_s"], g["lp_lane"])
+    assert np.array_equal(lx, g["lp_x"]) and np.array_equal(ly, g["lp_y"])
+    assert np.array_equal(lwp, g["lp_wp"]) and np.array_equal(ld, g["lp_dist"])
+    for nk in (3, 6, 13, 15):
+        out = oracle.spline(g[f"sp{nk}_kx"], g[f"sp{nk}_ky"], g[f"sp{nk}_q"])
+        assert np.array_equal(out, g[f"sp{nk}_out"]), nk
+    cs, cvs = g["lc_cars"]
+    es, evs, dt0 = g["lc_ego"]
+    out = oracle.lane_change(g["lc_id"], cs, cvs, g["lc_lane"], g["lc_el"], g["lc_tl"], es, evs, dt0)
+    assert np.array_equal(out, g["lc_out"])
+    assert len(set(out.tolist())) == 3
+    ls = oracle.limit_speed(*g["ls_in"], g["ls_inlane"])
+    for k, v in ls.items():
+        assert np.array_equal(v, g["ls_" + k]), k
+
+
+def test_oracle_starter_helpers_match_golden(oracle, golden_units, pp):
+    g = golden_units
+    csv = np.loadtxt(pp.MAP_CSV)
+    mx, my, ms = csv[:, 0].copy(), csv[:, 1].copy(), csv[:, 2].copy()
+    x, y, th = g["hw_xyth"]
+    assert np.array_equal(oracle.closest_waypoint(x, y, mx, my), g["hw_closest"])
+    assert np.array_equal(oracle.next_waypoint(x, y, th, mx, my), g["hw_next"])
+    assert np.array_equal(np.stack(oracle.get_frenet(x, y, th, mx, my)), g["hw_frenet"])
+    s, d = g["hw_sd"]
+    assert np.array_equal(np.stack(oracle.get_xy(s, d, ms, mx, my)), g["hw_xy"])
+
+
+# ---- live against the compiled reference (skipped where oracle/_ref is absent)
+
+@pytest.mark.parametrize("cars,n,seed", [(12, 6000, 1), (64, 600, 2), (0, 200, 3), (1, 400, 4)])
+def test_oracle_vs_reference_live(oracle, ref, pp, pmap, cars, n, seed):
+    fb = pp.synth_frames(pmap, n, cars, seed=seed, rare_permille=150, max_cars=max(cars, 1))
+    want = ref.plan(fb, want_flags=True)
+    got = oracle.plan(fb)
+    assert_plans_equal(plans_dict(got), plans_dict(want), ref.observable_flags, bitwise_traj=True)
+
+
+def test_map_tables_identical(oracle, ref, pmap):
+    assert np.array_equal(oracle.map_table(), ref.map_table())
+    assert np.array_equal(pmap.table(), ref.map_table())
+
+
+def test_glue_restatement_vs_untouched_lambda(ref, oracle, pp, pmap, abi):
+    """Closed loop of 60 frames fed (a) as JSON through the reference's untouched
+    onMessage lambda and (b) frame by frame through the class harness / oracle
+    with target_lane carried: agreement to the 15 significant digits of the
+    reference's JSON printer (src/json.hpp:6689-6692)."""
+    T = 60
+    base = pp.synth_frames(pmap, 1, 12, seed=77, rare_permille=0)
+    seq = abi.FrameBatch(T, 12)
+    tl = 1  # the reference starts with target_lane = 1 (src/main.cpp:1195)
+    cur = base
+    cur.prev_n[0] = 0
+    cur.ego_speed_mph[0] = 0.0
+    cur.target_lane_in[0] = tl
+    want_x = np.full((T, abi.PATH_LEN), np.nan)
+    want_y = np.full((T, abi.PATH_LEN), np.nan)
+    for t in range(T):
+        for k in seq.arrays():
+            getattr(seq, k)[t] = getattr(cur, k)[0]
+        p = oracle.plan(cur)
+        want_x[t], want_y[t] = p.next_x[0], p.next_y[0]
+        nxt = abi.FrameBatch(1, 12)
+        for k in cur.arrays():
+            getattr(nxt, k)[:] = getattr(cur, k)
+        consumed = 3
+        nxt.prev_n[0] = 50 - consumed
+        nxt.prev_x[0] = p.next_x[0, consumed:consumed + 10]
+        nxt.prev_y[0] = p.next_y[0, consumed:consumed + 10]
+        nxt.ego_x[0], nxt.ego_y[0] = p.next_x[0, consumed - 1], p.next_y[0, consumed - 1]
+        nxt.target_lane_in[0] = p.target_lane[0]
+        nxt.car_x[0] += nxt.car_vx[0] * 0.02 * consumed
+        nxt.car_y[0] += nxt.car_vy[0] * 0.02 * consumed
+        cur = nxt
+    ox, oy, on = ref.lambda_sequence(seq)
+    assert (on == 50).all()
+    assert np.nanmax(np.abs(ox - want_x) / np.abs(want_x)) < 5e-15
+    assert np.nanmax(np.abs(oy - want_y) / np.abs(want_y)) < 5e-15
