@@ -1,16 +1,29 @@
-// pp_plan.cu — the fused planning kernels and pp_plan_batch / pp_stats_batch.
+// pp_plan.cu — the planning kernels and pp_plan_batch / pp_stats_batch.
 //
-// One kernel launch plans a whole batch: every stage of the reference's
-// per-frame step (src/main.cpp:1254-1457) runs back to back in registers, the
-// map table sits in shared memory, and nothing intermediate touches HBM.
+// What bounds this path is the FP64 pipe, not HBM (1,520
+// algorithmic bytes against ~35-45 k FP64-heavy instructions per frame), and
+// most of those instructions sit in serial recurrences.  So every LANE carries
+// its own independent recurrence, and the step is cut into phases so that each
+// phase runs with the mapping that keeps its lanes converged:
 //
-// Mapping: the step is FP64-latency/issue bound, not HBM bound
-// (1,520 algorithmic bytes against ~35k dependent FP64 instructions per
-// frame), and ~85 % of those instructions sit in serial recurrences (segment
-// walks, the 40-step emission loop).  The throughput kernel therefore gives
-// every LANE its own frame, so the 32 lanes of a warp run 32 independent
-// recurrences; the blocks are persistent (grid = multiple of the SM count)
-// and stride over the batch.
+//   k_prep     one thread per FRAME : ego state (src/main.cpp:1254-1282),
+//              closest-waypoint scan + reference segment (:143-197), ego lane
+//              matching + speed projection (:1302-1313)
+//   k_cars     one thread per CAR   : Map::lane_matching + project_speed for
+//              every sensor-fusion object (:1325-1350) — 12x more parallel
+//              work items than frames, coalesced loads/stores
+//   k_plan     one thread per FRAME : LaneChangePlanner reductions, veto,
+//              followed cars, LimitSpeed, SpeedController (:1352-1438) and
+//              TrajectoryBuilder::build (:1446-1448, spline fit + emission)
+//
+// The few hundred bytes per frame that cross between phases go through a
+// stream-ordered scratch buffer in HBM (≈ 0.6 GB per 1M frames, ≈ 0.3 ms of
+// the ~10 ms step).  The ncu evidence that led here (the single fused kernel:
+// 45 % instruction-fetch stalls on 155 KB of SASS, 15 of 32 lanes active,
+// 51 % of warp instructions in the per-car walks at ~10 lanes) is in
+// profiles/r1_v0_*.  The fused single-kernel form is kept as variant 1: it
+// has the lowest latency for small batches and is the bitwise cross-check of
+// the pipeline (tests/test_gpu_parity.py).
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -24,49 +37,93 @@ using namespace ppd;
 
 constexpr int kBlock = 128;
 
-// Stage A: ego state, src/main.cpp:1254-1282.
-struct Ego {
-  double x, y, speed, acc, svx, svy, dt0;
-  int nprev;
+// ---------------------------------------------------------------------------
+// Stage A+B: ego state and reference segment (one frame).
+// ---------------------------------------------------------------------------
+struct FrameCtx {
+  double x, y, speed, acc;  // ego pose / Cartesian speed / clamped acceleration
+  int nprev;                // 0 or 10 kept points
+  RefState rs;
+  int lane;                 // ego lane (0 on match failure)
+  double s, d, vs, vd;
+  uint32_t flags;
 };
 
-PPD_INLINE Ego ego_state(const pp_frames &in, const pp_config &cfg, int64_t f, uint32_t &flags) {
-  Ego e;
-  e.x = in.ego_x[f];
-  e.y = in.ego_y[f];
-  e.speed = in.ego_speed_mph[f];
-  e.speed /= 2.237;  // :1239
-  e.acc = 0;
-  e.svx = 0;
-  e.svy = 0;
-  e.dt0 = 0;
-  e.nprev = 0;
-  if (in.prev_n[f] >= PP_PREV_KEEP) {  // :1261
+PPD_INLINE double ctx_dt0(const FrameCtx &c) { return c.nprev ? PP_PREV_KEEP / 50.0 : 0.0; }
+
+PPD_INLINE FrameCtx stage_prep(const MapView &m, const pp_config &cfg, const pp_frames &in,
+                               int64_t f) {
+  FrameCtx c;
+  c.flags = 0;
+  c.x = in.ego_x[f];
+  c.y = in.ego_y[f];
+  c.speed = in.ego_speed_mph[f];
+  c.speed /= 2.237;  // :1239
+  c.acc = 0;
+  c.nprev = 0;
+  double svx = 0, svy = 0;
+  if (in.prev_n[f] >= PP_PREV_KEEP) {  // :1261-1282
     const double *px = in.prev_x + f * PP_PREV_KEEP;
     const double *py = in.prev_y + f * PP_PREV_KEEP;
     const double p7x = px[7], p7y = py[7], p8x = px[8], p8y = py[8], p9x = px[9], p9y = py[9];
     const double v2 = vlen(p8x - p7x, p8y - p7y);
-    e.svx = p9x - p8x;
-    e.svy = p9y - p8y;
-    const double v3 = vlen(e.svx, e.svy);
-    e.acc = (v3 - v2) * 50;
-    e.speed = v3 * 50;
-    e.svx *= 50;
-    e.svy *= 50;
-    e.x = p9x;
-    e.y = p9y;
-    e.dt0 = PP_PREV_KEEP / 50.0;
-    e.nprev = PP_PREV_KEEP;
+    svx = p9x - p8x;
+    svy = p9y - p8y;
+    const double v3 = vlen(svx, svy);
+    c.acc = (v3 - v2) * 50;
+    c.speed = v3 * 50;
+    svx *= 50;
+    svy *= 50;
+    c.x = p9x;
+    c.y = p9y;
+    c.nprev = PP_PREV_KEEP;
   } else {
-    flags |= PP_F_COLD_START;
+    c.flags |= PP_F_COLD_START;
   }
-  // the clamp of :1319-1320 is applied by the caller after project_speed (it
-  // only feeds LimitSpeed)
-  (void)cfg;
-  return e;
+  init_reference(m, c.x, c.y, c.rs);  // :1299
+  Match em = lane_match(m, c.rs, c.x, c.y);  // :1302-1307
+  if (!em.ok) {
+    c.flags |= PP_F_EGO_MATCH_FAIL;
+    em.s = 0;
+    em.d = 0;
+    em.lane = 0;
+  }
+  c.lane = em.lane;
+  c.s = em.s;
+  c.d = em.d;
+  project_speed(m, svx, svy, c.rs.wp, c.vs, c.vd);  // :1313
+  if (c.acc > cfg.maximum_acc) c.acc = cfg.maximum_acc;  // :1319-1320
+  if (c.acc < -cfg.maximum_acc) c.acc = -cfg.maximum_acc;
+  return c;
 }
 
-// Followed-car candidate: (s0, id) lexicographic minimum, == the reference's
+// ---------------------------------------------------------------------------
+// Stage C: one sensor-fusion object (:1336-1343).
+// ---------------------------------------------------------------------------
+struct CarRes {
+  int lane, wp;  // lane = -1: dropped (:1339)
+  double s, d, vs, vd;
+};
+
+PPD_INLINE CarRes stage_car(const MapView &m, const RefState &rs, double x, double y, double vx,
+                            double vy) {
+  CarRes r;
+  const Match cm = lane_match(m, rs, x, y);
+  r.lane = cm.ok ? cm.lane : -1;
+  r.wp = cm.ok ? cm.wp : 0;
+  r.s = cm.s;
+  r.d = cm.d;
+  r.vs = 0;
+  r.vd = 0;
+  if (cm.ok) project_speed(m, vx, vy, cm.wp, r.vs, r.vd);
+  return r;
+}
+
+// ---------------------------------------------------------------------------
+// Stage D+E: streaming reductions over the cars of a frame
+// (:377-445 LaneChangePlanner loop, :1388-1410 followed cars).
+// ---------------------------------------------------------------------------
+// Followed-car candidate: (s0, id) lexicographic minimum == the reference's
 // "first car in ascending id order with strictly smaller s0" (:1395,1404).
 struct Cand {
   double s0;
@@ -85,138 +142,286 @@ PPD_INLINE void cand_offer(Cand &c, double s0, int id, int j) {
   }
 }
 
-// The whole planning step for frame f, executed by ONE thread.
-__device__ void plan_frame(const MapView &m, const pp_config &cfg, const pp_frames &in,
-                           const pp_plans &out, int64_t f) {
-  uint32_t flags = 0;
-  Ego e = ego_state(in, cfg, f, flags);
-
-  RefState rs;
-  init_reference(m, e.x, e.y, rs);  // :1299
-
-  Match em = lane_match(m, rs, e.x, e.y);  // :1302-1307
-  if (!em.ok) {
-    flags |= PP_F_EGO_MATCH_FAIL;
-    em.s = 0;
-    em.d = 0;
-    em.lane = 0;
-  }
-  double evs, evd;
-  project_speed(m, e.svx, e.svy, rs.wp, evs, evd);  // :1313
-  if (e.acc > cfg.maximum_acc) e.acc = cfg.maximum_acc;  // :1319-1320
-  if (e.acc < -cfg.maximum_acc) e.acc = -cfg.maximum_acc;
-
-  // ---- sensor fusion, one streaming pass (:1325-1350 + :377-445 + :1388-1410)
-  const int mc = in.max_cars;
-  int nc = in.n_cars[f];
-  if (nc > mc) nc = mc;
-  const int tl_in = in.target_lane_in[f];
+struct Behav {
   LaneStats ls;
-  lane_stats_init(ls, cfg);
   Cand own, tl0, tl1, tl2;
-  cand_init(own);
-  cand_init(tl0);
-  cand_init(tl1);
-  cand_init(tl2);
-  const double behind = em.s - cfg.car_length - cfg.safety_distance;  // :1402
-  const int64_t cb = f * mc;
-  for (int j = 0; j < nc; j++) {
-    const int id = in.car_id[cb + j];
-    const double x = in.car_x[cb + j], y = in.car_y[cb + j];
-    const double vx = in.car_vx[cb + j], vy = in.car_vy[cb + j];
-    const Match cm = lane_match(m, rs, x, y);
-    double vs = 0, vd = 0;
-    if (cm.ok) project_speed(m, vx, vy, cm.wp, vs, vd);
-    if (out.car_lane) out.car_lane[cb + j] = cm.ok ? cm.lane : -1;
-    if (out.car_next_wp) out.car_next_wp[cb + j] = cm.ok ? cm.wp : 0;
-    if (out.car_s) out.car_s[cb + j] = cm.s;
-    if (out.car_d) out.car_d[cb + j] = cm.d;
-    if (out.car_vs) out.car_vs[cb + j] = vs;
-    if (out.car_vd) out.car_vd[cb + j] = vd;
-    if (!cm.ok) {  // :1336-1340 dropped from the map
-      flags |= PP_F_CAR_DROPPED;
-      continue;
-    }
-    lane_stats_add(ls, cfg, id, cm.lane, cm.s, vs, em.lane, tl_in, em.s, evs, e.dt0, flags);
-    const double s0 = cm.s + vs * e.dt0;
-    const double d0 = cm.d + vd * e.dt0;
-    if (s0 > em.s && fabs(d0 - em.d) < 3) cand_offer(own, s0, id, j);
-    if (s0 >= behind) {
-      if (fabs(d0 - lane_center_offset(0)) < 3) cand_offer(tl0, s0, id, j);
-      if (fabs(d0 - lane_center_offset(1)) < 3) cand_offer(tl1, s0, id, j);
-      if (fabs(d0 - lane_center_offset(2)) < 3) cand_offer(tl2, s0, id, j);
-    }
+};
+PPD_INLINE void behav_init(Behav &b, const pp_config &cfg) {
+  lane_stats_init(b.ls, cfg);
+  cand_init(b.own);
+  cand_init(b.tl0);
+  cand_init(b.tl1);
+  cand_init(b.tl2);
+}
+PPD_INLINE void behav_add(Behav &b, const pp_config &cfg, const FrameCtx &c, int tl_in, int id,
+                          int j, const CarRes &car, uint32_t &flags) {
+  if (car.lane < 0) {  // :1336-1340 dropped from the map
+    flags |= PP_F_CAR_DROPPED;
+    return;
   }
+  const double dt0 = ctx_dt0(c);
+  lane_stats_add(b.ls, cfg, id, car.lane, car.s, car.vs, c.lane, tl_in, c.s, c.vs, dt0, flags);
+  const double s0 = car.s + car.vs * dt0;
+  const double d0 = car.d + car.vd * dt0;
+  if (s0 > c.s && fabs(d0 - c.d) < 3) cand_offer(b.own, s0, id, j);
+  if (s0 >= c.s - cfg.car_length - cfg.safety_distance) {  // :1402
+    if (fabs(d0 - lane_center_offset(0)) < 3) cand_offer(b.tl0, s0, id, j);
+    if (fabs(d0 - lane_center_offset(1)) < 3) cand_offer(b.tl1, s0, id, j);
+    if (fabs(d0 - lane_center_offset(2)) < 3) cand_offer(b.tl2, s0, id, j);
+  }
+}
 
-  // ---- lane decision (:1355) + veto (:1358-1369)
-  int target_lane = lane_stats_decide(ls, cfg, em.lane, tl_in);
-  if (target_lane != em.lane) {
+// ---------------------------------------------------------------------------
+// Stage D..I tail: decision, speed target, trajectory, outputs (one frame).
+// ---------------------------------------------------------------------------
+PPD_INLINE void stage_finish(const MapView &m, const pp_config &cfg, const pp_frames &in,
+                             const pp_plans &out, int64_t f, const FrameCtx &c, const Behav &b,
+                             int tl_in, uint32_t flags) {
+  const int64_t cb = f * in.max_cars;
+  // lane decision (:1355) + veto (:1358-1369)
+  int target_lane = lane_stats_decide(b.ls, cfg, c.lane, tl_in);
+  if (target_lane != c.lane) {
     const double dtl = lane_center_offset(target_lane);
-    const double diff = fabs(evd * 1.0 + em.d - dtl);
+    const double diff = fabs(c.vd * 1.0 + c.d - dtl);
     if (diff > 6.0) {
       flags |= PP_F_VETO;
-      target_lane = em.lane;
+      target_lane = c.lane;
     }
   }
-  Cand tl = target_lane == 0 ? tl0 : (target_lane == 1 ? tl1 : tl2);
-  if (tl.id == own.id) tl.id = -1;  // :1411 only check once
+  Cand tl = target_lane == 0 ? b.tl0 : (target_lane == 1 ? b.tl1 : b.tl2);
+  if (tl.id == b.own.id) tl.id = -1;  // :1411 only check once
 
-  // ---- speed target (:1422-1438)
+  // speed target (:1422-1438)
   SpeedCtl sc;
-  sc_init(sc, cfg, e.speed);
-  if (own.id != -1) {
+  sc_init(sc, cfg, c.speed);
+  if (b.own.id != -1) {
     double ts, tt;
-    limit_speed(cfg, in.car_vx[cb + own.j], in.car_vy[cb + own.j], own.s0, em.s, e.speed, e.acc,
-                true, ts, tt, flags);
+    limit_speed(cfg, in.car_vx[cb + b.own.j], in.car_vy[cb + b.own.j], b.own.s0, c.s, c.speed,
+                c.acc, true, ts, tt, flags);
     sc_limit(sc, ts, tt);
   }
   if (tl.id != -1) {
     double ts, tt;
-    limit_speed(cfg, in.car_vx[cb + tl.j], in.car_vy[cb + tl.j], tl.s0, em.s, e.speed, e.acc,
-                false, ts, tt, flags);
+    limit_speed(cfg, in.car_vx[cb + tl.j], in.car_vy[cb + tl.j], tl.s0, c.s, c.speed, c.acc, false,
+                ts, tt, flags);
     sc_limit(sc, ts, tt);
   }
   if (out.target_speed) out.target_speed[f] = sc.target;
   if (out.target_time) out.target_time[f] = sc.time;
 
-  // ---- trajectory (:1446-1448)
-  const int np = build_trajectory(m, cfg, rs, in.prev_x + f * PP_PREV_KEEP,
-                                  in.prev_y + f * PP_PREV_KEEP, e.nprev, e.x, e.y,
-                                  in.ego_yaw_deg[f], target_lane, em.d, evd, sc,
+  // trajectory (:1446-1448)
+  const int np = build_trajectory(m, cfg, c.rs, in.prev_x + f * PP_PREV_KEEP,
+                                  in.prev_y + f * PP_PREV_KEEP, c.nprev, c.x, c.y,
+                                  in.ego_yaw_deg[f], target_lane, c.d, c.vd, sc,
                                   out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN, flags);
-
   for (int i = np; i < PP_PATH_LEN; i++) {  // short (fallback) paths: pad with NaN
     out.next_x[f * PP_PATH_LEN + i] = __longlong_as_double(0x7ff8000000000000ll);
     out.next_y[f * PP_PATH_LEN + i] = __longlong_as_double(0x7ff8000000000000ll);
   }
   out.n_points[f] = np;
-  out.ego_lane[f] = em.lane;
-  out.ref_wp[f] = rs.wp;
+  out.ego_lane[f] = c.lane;
+  out.ref_wp[f] = c.rs.wp;
   out.target_lane[f] = target_lane;
   out.flags[f] = flags;
-  if (out.ego_s) out.ego_s[f] = em.s;
-  if (out.ego_d) out.ego_d[f] = em.d;
-  if (out.ego_vs) out.ego_vs[f] = evs;
-  if (out.ego_vd) out.ego_vd[f] = evd;
-  if (out.ego_speed) out.ego_speed[f] = e.speed;
-  if (out.ego_acc) out.ego_acc[f] = e.acc;
-  if (out.next_car_id) out.next_car_id[f] = own.id;
+  if (out.ego_s) out.ego_s[f] = c.s;
+  if (out.ego_d) out.ego_d[f] = c.d;
+  if (out.ego_vs) out.ego_vs[f] = c.vs;
+  if (out.ego_vd) out.ego_vd[f] = c.vd;
+  if (out.ego_speed) out.ego_speed[f] = c.speed;
+  if (out.ego_acc) out.ego_acc[f] = c.acc;
+  if (out.next_car_id) out.next_car_id[f] = b.own.id;
   if (out.next_car_in_target_lane) out.next_car_in_target_lane[f] = tl.id;
 }
 
-// Throughput mapping: one thread (lane) per frame, persistent blocks.
+PPD_INLINE void store_car(const pp_plans &out, int64_t slot, const CarRes &r) {
+  if (out.car_lane) out.car_lane[slot] = r.lane;
+  if (out.car_next_wp) out.car_next_wp[slot] = r.wp;
+  if (out.car_s) out.car_s[slot] = r.s;
+  if (out.car_d) out.car_d[slot] = r.d;
+  if (out.car_vs) out.car_vs[slot] = r.vs;
+  if (out.car_vd) out.car_vd[slot] = r.vd;
+}
+
+// ===========================================================================
+// Variant 1: everything in one kernel, one thread per frame.
+// ===========================================================================
 __global__ void __launch_bounds__(kBlock)
-plan_thread_per_frame(const double *__restrict__ map_table, int n_wp,
-                      const __grid_constant__ pp_config cfg, const __grid_constant__ pp_frames in,
-                      const __grid_constant__ pp_plans out, int64_t n_frames) {
+plan_fused(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
+           const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
+           int64_t n_frames) {
   extern __shared__ double s_map[];
-  const int words = n_wp * PP_MAP_STRIDE;
-  for (int i = threadIdx.x; i < words; i += blockDim.x) s_map[i] = map_table[i];
-  __syncthreads();
-  MapView m{s_map, n_wp};
+  const MapView m = stage_map(s_map, map_table, n_wp);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_frames; f += stride)
-    plan_frame(m, cfg, in, out, f);
+  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_frames; f += stride) {
+    const FrameCtx c = stage_prep(m, cfg, in, f);
+    uint32_t flags = c.flags;
+    const int mc = in.max_cars;
+    int nc = in.n_cars[f];
+    if (nc > mc) nc = mc;
+    const int tl_in = in.target_lane_in[f];
+    Behav b;
+    behav_init(b, cfg);
+    const int64_t cb = f * mc;
+    for (int j = 0; j < nc; j++) {
+      const CarRes r = stage_car(m, c.rs, in.car_x[cb + j], in.car_y[cb + j], in.car_vx[cb + j],
+                                 in.car_vy[cb + j]);
+      store_car(out, cb + j, r);
+      behav_add(b, cfg, c, tl_in, in.car_id[cb + j], j, r, flags);
+    }
+    stage_finish(m, cfg, in, out, f, c, b, tl_in, flags);
+  }
+}
+
+// ===========================================================================
+// Variant 2: the three-phase pipeline.
+// ===========================================================================
+// Per-chunk scratch in HBM (SoA, one entry per frame / per car slot).
+struct Scratch {
+  double *x, *y, *speed, *acc, *s, *d, *vs, *vd, *ratio;  // ratio: [3][n]
+  int32_t *wp, *lane, *nprev;
+  uint32_t *flags;
+  double *car_s, *car_d, *car_vs, *car_vd;  // [n][max_cars]
+  int32_t *car_lane, *car_wp;
+  int64_t n;  // frames in this chunk (stride of ratio)
+};
+
+size_t scratch_bytes(int64_t n, int mc) {
+  const size_t per_frame = 11 * 8 + 4 * 4;
+  const size_t per_car = 4 * 8 + 2 * 4;
+  return (size_t)n * (per_frame + (size_t)mc * per_car) + 64 * 32;
+}
+
+Scratch carve_scratch(char *base, int64_t n, int mc) {
+  Scratch s;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char *p = base + off;
+    off += (bytes + 255) & ~(size_t)255;
+    return p;
+  };
+  const size_t N = (size_t)n, NC = (size_t)n * (size_t)mc;
+  s.x = (double *)take(N * 8);
+  s.y = (double *)take(N * 8);
+  s.speed = (double *)take(N * 8);
+  s.acc = (double *)take(N * 8);
+  s.s = (double *)take(N * 8);
+  s.d = (double *)take(N * 8);
+  s.vs = (double *)take(N * 8);
+  s.vd = (double *)take(N * 8);
+  s.ratio = (double *)take(3 * N * 8);
+  s.wp = (int32_t *)take(N * 4);
+  s.lane = (int32_t *)take(N * 4);
+  s.nprev = (int32_t *)take(N * 4);
+  s.flags = (uint32_t *)take(N * 4);
+  s.car_s = (double *)take(NC * 8);
+  s.car_d = (double *)take(NC * 8);
+  s.car_vs = (double *)take(NC * 8);
+  s.car_vd = (double *)take(NC * 8);
+  s.car_lane = (int32_t *)take(NC * 4);
+  s.car_wp = (int32_t *)take(NC * 4);
+  s.n = n;
+  return s;
+}
+
+// `in` / `out` already point at the first frame of the chunk.
+__global__ void __launch_bounds__(kBlock)
+k_prep(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
+       const __grid_constant__ pp_frames in, const __grid_constant__ Scratch sc, int64_t n) {
+  extern __shared__ double s_map[];
+  const MapView m = stage_map(s_map, map_table, n_wp);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += stride) {
+    const FrameCtx c = stage_prep(m, cfg, in, f);
+    sc.x[f] = c.x;
+    sc.y[f] = c.y;
+    sc.speed[f] = c.speed;
+    sc.acc[f] = c.acc;
+    sc.s[f] = c.s;
+    sc.d[f] = c.d;
+    sc.vs[f] = c.vs;
+    sc.vd[f] = c.vd;
+    sc.ratio[f] = c.rs.ratio[0];
+    sc.ratio[sc.n + f] = c.rs.ratio[1];
+    sc.ratio[2 * sc.n + f] = c.rs.ratio[2];
+    sc.wp[f] = c.rs.wp;
+    sc.lane[f] = c.lane;
+    sc.nprev[f] = c.nprev;
+    sc.flags[f] = c.flags;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_cars(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_frames in,
+       const __grid_constant__ pp_plans out, const __grid_constant__ Scratch sc, int64_t n) {
+  extern __shared__ double s_map[];
+  const MapView m = stage_map(s_map, map_table, n_wp);
+  const int mc = in.max_cars;
+  const int64_t total = n * mc;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t f = t / mc;
+    const int j = (int)(t - f * mc);
+    if (j >= in.n_cars[f]) continue;
+    RefState rs;
+    rs.wp = sc.wp[f];
+    rs.ratio[0] = sc.ratio[f];
+    rs.ratio[1] = sc.ratio[sc.n + f];
+    rs.ratio[2] = sc.ratio[2 * sc.n + f];
+    const CarRes r = stage_car(m, rs, in.car_x[t], in.car_y[t], in.car_vx[t], in.car_vy[t]);
+    sc.car_s[t] = r.s;
+    sc.car_d[t] = r.d;
+    sc.car_vs[t] = r.vs;
+    sc.car_vd[t] = r.vd;
+    sc.car_lane[t] = r.lane;
+    sc.car_wp[t] = r.wp;
+    store_car(out, t, r);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_plan(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
+       const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
+       const __grid_constant__ Scratch sc, int64_t n) {
+  extern __shared__ double s_map[];
+  const MapView m = stage_map(s_map, map_table, n_wp);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += stride) {
+    FrameCtx c;
+    c.x = sc.x[f];
+    c.y = sc.y[f];
+    c.speed = sc.speed[f];
+    c.acc = sc.acc[f];
+    c.s = sc.s[f];
+    c.d = sc.d[f];
+    c.vs = sc.vs[f];
+    c.vd = sc.vd[f];
+    c.rs.ratio[0] = sc.ratio[f];
+    c.rs.ratio[1] = sc.ratio[sc.n + f];
+    c.rs.ratio[2] = sc.ratio[2 * sc.n + f];
+    c.rs.wp = sc.wp[f];
+    c.lane = sc.lane[f];
+    c.nprev = sc.nprev[f];
+    c.flags = sc.flags[f];
+    uint32_t flags = c.flags;
+    const int mc = in.max_cars;
+    int nc = in.n_cars[f];
+    if (nc > mc) nc = mc;
+    const int tl_in = in.target_lane_in[f];
+    Behav b;
+    behav_init(b, cfg);
+    const int64_t cb = f * mc;
+    for (int j = 0; j < nc; j++) {
+      CarRes r;
+      r.lane = sc.car_lane[cb + j];
+      r.wp = sc.car_wp[cb + j];
+      r.s = sc.car_s[cb + j];
+      r.d = sc.car_d[cb + j];
+      r.vs = sc.car_vs[cb + j];
+      r.vd = sc.car_vd[cb + j];
+      behav_add(b, cfg, c, tl_in, in.car_id[cb + j], j, r, flags);
+    }
+    stage_finish(m, cfg, in, out, f, c, b, tl_in, flags);
+  }
 }
 
 // ---- aggregate statistics: exact int64 sums -----------------
@@ -274,6 +479,78 @@ int check_launch(const char *what) {
   return PP_OK;
 }
 
+// persistent grid: enough blocks for `items`, capped at a whole number of waves
+int grid_for(int64_t items, int blocks_per_sm) {
+  const int64_t want = (items + kBlock - 1) / kBlock;
+  const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+  return (int)(want < cap ? want : cap);
+}
+
+// pp_frames / pp_plans advanced by `lo` frames
+pp_frames offset_frames(const pp_frames &a, int64_t lo) {
+  pp_frames r = a;
+  const int64_t mc = a.max_cars;
+  r.ego_x += lo;
+  r.ego_y += lo;
+  r.ego_yaw_deg += lo;
+  r.ego_speed_mph += lo;
+  r.prev_n += lo;
+  r.prev_x += lo * PP_PREV_KEEP;
+  r.prev_y += lo * PP_PREV_KEEP;
+  r.target_lane_in += lo;
+  r.n_cars += lo;
+  if (r.car_id) r.car_id += lo * mc;
+  if (r.car_x) r.car_x += lo * mc;
+  if (r.car_y) r.car_y += lo * mc;
+  if (r.car_vx) r.car_vx += lo * mc;
+  if (r.car_vy) r.car_vy += lo * mc;
+  return r;
+}
+template <class T>
+void adv(T *&p, int64_t k) {
+  if (p) p += k;
+}
+pp_plans offset_plans(const pp_plans &a, int64_t lo, int64_t mc) {
+  pp_plans r = a;
+  adv(r.next_x, lo * PP_PATH_LEN);
+  adv(r.next_y, lo * PP_PATH_LEN);
+  adv(r.n_points, lo);
+  adv(r.ego_lane, lo);
+  adv(r.ref_wp, lo);
+  adv(r.target_lane, lo);
+  adv(r.flags, lo);
+  adv(r.ego_s, lo);
+  adv(r.ego_d, lo);
+  adv(r.ego_vs, lo);
+  adv(r.ego_vd, lo);
+  adv(r.ego_speed, lo);
+  adv(r.ego_acc, lo);
+  adv(r.target_speed, lo);
+  adv(r.target_time, lo);
+  adv(r.next_car_id, lo);
+  adv(r.next_car_in_target_lane, lo);
+  adv(r.car_s, lo * mc);
+  adv(r.car_d, lo * mc);
+  adv(r.car_vs, lo * mc);
+  adv(r.car_vd, lo * mc);
+  adv(r.car_lane, lo * mc);
+  adv(r.car_next_wp, lo * mc);
+  return r;
+}
+
+constexpr int64_t kPipeChunk = 1 << 18;  // frames per scratch buffer (≈ 155 MB at 12 cars)
+constexpr int64_t kFusedBelow = 4096;    // auto: batches this small go through the fused kernel
+
+template <class K>
+int ensure_smem(K kernel, size_t smem) {
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return check_launch("cudaFuncSetAttribute");
+  }
+  return PP_OK;
+}
+
 }  // namespace
 
 extern "C" int pp_set_kernel_variant(int variant) {
@@ -300,23 +577,48 @@ extern "C" int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_f
     return PP_E_ARG;
   if (n_frames == 0) return PP_OK;
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  const size_t smem = (size_t)map->n * PP_MAP_STRIDE * sizeof(double);
+  const size_t smem = map_smem_doubles(map->n) * sizeof(double);
   if (smem > 200 * 1024) return PP_E_RANGE;
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
-    cudaFuncSetAttribute(plan_thread_per_frame, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
-    attr_set = true;
+  int rc;
+  if ((rc = ensure_smem(plan_fused, smem)) != PP_OK) return rc;
+  if ((rc = ensure_smem(k_prep, smem)) != PP_OK) return rc;
+  if ((rc = ensure_smem(k_cars, smem)) != PP_OK) return rc;
+  if ((rc = ensure_smem(k_plan, smem)) != PP_OK) return rc;
+
+  const bool fused = g_variant == 1 || (g_variant == 0 && n_frames < kFusedBelow);
+  if (fused) {
+    plan_fused<<<grid_for(n_frames, 8), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, *in, *out,
+                                                            n_frames);
+    ppi::count_launch();
+    return check_launch("plan_fused");
   }
-  // persistent grid: a whole number of waves over the SMs, capped by the batch
-  const int sms = sm_count();
-  int64_t want = (n_frames + kBlock - 1) / kBlock;
-  int64_t cap = (int64_t)sms * 8;
-  int grid = (int)(want < cap ? want : cap);
-  plan_thread_per_frame<<<grid, kBlock, smem, st>>>(map->dev_table, map->n, *cfg, *in, *out,
-                                                    n_frames);
-  ppi::count_launch();
-  return check_launch("plan_thread_per_frame");
+
+  const int mc = in->max_cars;
+  const int64_t chunk = n_frames < kPipeChunk ? n_frames : kPipeChunk;
+  char *buf = nullptr;
+  cudaError_t e = cudaMallocAsync((void **)&buf, scratch_bytes(chunk, mc), st);
+  if (e != cudaSuccess) {
+    ppi::set_cuda_error("cudaMallocAsync(scratch)", (int)e, cudaGetErrorString(e));
+    cudaGetLastError();
+    return PP_E_CUDA;
+  }
+  const Scratch sc = carve_scratch(buf, chunk, mc);
+  rc = PP_OK;
+  for (int64_t lo = 0; lo < n_frames && rc == PP_OK; lo += chunk) {
+    const int64_t cnt = (n_frames - lo) < chunk ? (n_frames - lo) : chunk;
+    const pp_frames fin = offset_frames(*in, lo);
+    const pp_plans fout = offset_plans(*out, lo, mc);
+    k_prep<<<grid_for(cnt, 12), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, fin, sc, cnt);
+    if (mc > 0)
+      k_cars<<<grid_for(cnt * mc, 12), kBlock, smem, st>>>(map->dev_table, map->n, fin, fout, sc,
+                                                           cnt);
+    k_plan<<<grid_for(cnt, 12), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, fin, fout, sc,
+                                                    cnt);
+    ppi::count_launch(mc > 0 ? 3 : 2);
+    rc = check_launch("plan pipeline");
+  }
+  cudaFreeAsync(buf, st);
+  return rc;
 }
 
 extern "C" int pp_stats_batch(const pp_plans *p, int64_t n_frames, int64_t *stats_dev,

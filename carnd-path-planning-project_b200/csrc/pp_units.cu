@@ -27,18 +27,12 @@ __global__ void k_pt_seg(const double *px, const double *py, const double *ax, c
   snom[i] = s.snom;
 }
 
-__device__ void stage_map(double *s_map, const double *table, int n_wp) {
-  for (int i = threadIdx.x; i < n_wp * PP_MAP_STRIDE; i += blockDim.x) s_map[i] = table[i];
-  __syncthreads();
-}
-
 __global__ void k_init_reference(const double *table, int n_wp, const double *x, const double *y,
                                  int32_t *wp, double *ratio, int64_t n) {
   extern __shared__ double s_map[];
-  stage_map(s_map, table, n_wp);
+  const MapView m = stage_map(s_map, table, n_wp);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  MapView m{s_map, n_wp};
   RefState rs;
   init_reference(m, x[i], y[i], rs);
   wp[i] = rs.wp;
@@ -52,10 +46,9 @@ __global__ void k_lane_matching(const double *table, int n_wp, const double *rx,
                                 const double *vy, int32_t *ok, int32_t *lane, int32_t *next_wp,
                                 double *s, double *d, double *vs, double *vd, int64_t n) {
   extern __shared__ double s_map[];
-  stage_map(s_map, table, n_wp);
+  const MapView m = stage_map(s_map, table, n_wp);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  MapView m{s_map, n_wp};
   RefState rs;
   init_reference(m, rx[i], ry[i], rs);
   const Match mt = lane_match(m, rs, x[i], y[i]);
@@ -74,10 +67,9 @@ __global__ void k_lane_pos(const double *table, int n_wp, const double *rx, cons
                            const double *s, const int32_t *lane, double *ox, double *oy,
                            int32_t *owp, double *odist, int64_t n) {
   extern __shared__ double s_map[];
-  stage_map(s_map, table, n_wp);
+  const MapView m = stage_map(s_map, table, n_wp);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  MapView m{s_map, n_wp};
   RefState rs;
   init_reference(m, rx[i], ry[i], rs);
   double qx, qy, dist;
@@ -134,7 +126,7 @@ int finish(const char *what) {
   return PP_OK;
 }
 inline int grid_for(int64_t n) { return (int)((n + kB - 1) / kB); }
-inline size_t map_smem(const pp_map *m) { return (size_t)m->n * PP_MAP_STRIDE * sizeof(double); }
+inline size_t map_smem(const pp_map *m) { return map_smem_doubles(m->n) * sizeof(double); }
 int need_map(const pp_map *m, const char *who) {
   if (!m) return PP_E_ARG;
   if (!m->dev_table) {
