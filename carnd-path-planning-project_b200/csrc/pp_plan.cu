@@ -595,6 +595,21 @@ extern "C" int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_f
 
   const int mc = in->max_cars;
   const int64_t chunk = n_frames < kPipeChunk ? n_frames : kPipeChunk;
+  {  // keep freed scratch inside the stream-ordered pool (default threshold 0 hands it back to
+     // the driver at every synchronisation, which costs milliseconds per call)
+    static bool pool_tuned[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !pool_tuned[dev]) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+      pool_tuned[dev] = true;
+    }
+  }
   char *buf = nullptr;
   cudaError_t e = cudaMallocAsync((void **)&buf, scratch_bytes(chunk, mc), st);
   if (e != cudaSuccess) {

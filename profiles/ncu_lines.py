@@ -39,7 +39,13 @@ for f in os.listdir(tmp):
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
                      capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(raw)))
+allrows = list(csv.reader(io.StringIO(raw)))
+# a report may hold several kernels: keep the section whose name matches
+starts = [i for i, r in enumerate(allrows) if r and r[0] == "Kernel Name"]
+sel = [i for i in starts if kern in allrows[i][1]]
+lo = sel[0] if sel else starts[0]
+hi = min([i for i in starts if i > lo] + [len(allrows)])
+rows = allrows[lo:hi]
 h = rows[1]
 ia, isamp, iinst, ithr = h.index("Address"), h.index("# Samples"), h.index("Instructions Executed"), h.index("Thread Instructions Executed")
 ino = h.index("stall_no_inst")

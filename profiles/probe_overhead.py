@@ -1,0 +1,22 @@
+"""Host-side vs device-side time of pp_plan_batch (diagnostic)."""
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from __graft_entry__ import load_package
+pp = load_package()
+v = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
+pp.set_kernel_variant(v)
+m = pp.Map()
+fr = pp.synth_frames(m, n, 12)
+df = pp.DeviceFrames(fr); dp = pp.DevicePlans(n, 12, diag=True, cars=False)
+for _ in range(3): pp.plan_batch(m, df, dp)
+torch.cuda.synchronize()
+for rep in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); e0.record()
+    for _ in range(5): pp.plan_batch(m, df, dp)
+    e1.record(); t1 = time.perf_counter()
+    torch.cuda.synchronize(); t2 = time.perf_counter()
+    print(f"variant {v} n {n}: host issue {1e3*(t1-t0)/5:.3f} ms/call, device {e0.elapsed_time(e1)/5:.3f} ms/call, wall {1e3*(t2-t0)/5:.3f} ms/call")
