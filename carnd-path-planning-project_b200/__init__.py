@@ -32,7 +32,7 @@ EXPORTS = [
     "pp_set_kernel_variant", "pp_launch_count", "pp_distancesq_pt_seg_batch",
     "pp_init_reference_waypoint_batch", "pp_lane_matching_batch", "pp_get_lane_pos_batch",
     "pp_spline_batch", "pp_closest_waypoint_batch", "pp_next_waypoint_batch",
-    "pp_get_frenet_batch", "pp_get_xy_batch", "pp_synth_frames",
+    "pp_get_frenet_batch", "pp_get_xy_batch", "pp_synth_frames", "pp_selftest_math",
 ]
 
 

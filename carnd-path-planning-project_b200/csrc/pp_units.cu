@@ -116,6 +116,53 @@ __global__ void k_get_xy(const double *s, const double *d, const double *ms, con
   if (i < n) get_xy(s[i], d[i], ms, mx, my, nwp, ox[i], oy[i]);
 }
 
+// Self-test of the exact-arithmetic helpers of pp_device.cuh against the generic
+// operations they replace: counts[0] div_by != a/b, counts[1] div50 != a/50,
+// counts[2] fmod_near != fmod, counts[3] max |atan2_step - atan2| in ulps.
+__device__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ double rnd_double(unsigned long long &st, int min_exp, int max_exp) {
+  st = mix64(st);
+  const unsigned long long mant = st & 0xFFFFFFFFFFFFFull;
+  st = mix64(st);
+  const int e = min_exp + (int)(st % (unsigned long long)(max_exp - min_exp + 1));
+  const unsigned long long sign = (st >> 40) & 1ull;
+  const unsigned long long bits = (sign << 63) | ((unsigned long long)(e + 1023) << 52) | mant;
+  return __longlong_as_double((long long)bits);
+}
+__global__ void k_selftest_math(int64_t n, unsigned long long seed, unsigned long long *counts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long st = mix64(seed ^ (unsigned long long)i * 0xD1B54A32D192ED03ull);
+  // ordinary magnitudes most of the time, extreme ones sometimes (guards must route them)
+  const bool wide = (i & 15) == 0;
+  const double a = rnd_double(st, wide ? -1000 : -40, wide ? 1000 : 40);
+  const double b = rnd_double(st, wide ? -1000 : -40, wide ? 1000 : 40);
+  const Rcp r = rcp_make(b);
+  const double q = div_by(a, r), qe = a / b;
+  if (__double_as_longlong(q) != __double_as_longlong(qe)) atomicAdd(&counts[0], 1ull);
+  const double h = div50(a), he = a / 50.0;
+  if (__double_as_longlong(h) != __double_as_longlong(he)) atomicAdd(&counts[1], 1ull);
+  st = mix64(st);
+  const double x = -2.0 + 34.0 * ((double)(st >> 11) * (1.0 / 9007199254740992.0));
+  const double m = 2 * PPD_PI;
+  const double f = fmod_near(x, m), fe = fmod(x, m);
+  if (__double_as_longlong(f) != __double_as_longlong(fe)) atomicAdd(&counts[2], 1ull);
+  st = mix64(st);
+  const double dx = 0.001 + 0.5 * ((double)(st >> 11) * (1.0 / 9007199254740992.0));
+  st = mix64(st);
+  const double dy = dx * 0.3 * (2.0 * ((double)(st >> 11) * (1.0 / 9007199254740992.0)) - 1.0);
+  const double t1 = atan2_step(dy, dx), t2 = atan2(dy, dx);
+  long long d = __double_as_longlong(t1) - __double_as_longlong(t2);
+  if (d < 0) d = -d;
+  if ((t1 < 0) != (t2 < 0) && t1 != t2) d = 1000;  // different signs: flag loudly
+  atomicMax(&counts[3], (unsigned long long)d);
+}
+
 int finish(const char *what) {
   ppi::count_launch();
   cudaError_t e = cudaGetLastError();
@@ -204,6 +251,16 @@ int pp_spline_batch(const double *kx, const double *ky, int32_t n_knots, const d
   k_spline<<<grid_for(n_splines), kB, 0, (cudaStream_t)stream>>>(kx, ky, n_knots, q, n_q, out,
                                                                  n_splines);
   return finish("k_spline");
+}
+
+int pp_selftest_math(int64_t n, uint64_t seed, int64_t *counts_dev, void *stream) {
+  if (!counts_dev || n < 0) return PP_E_ARG;
+  if (cudaMemsetAsync(counts_dev, 0, 4 * sizeof(int64_t), (cudaStream_t)stream) != cudaSuccess)
+    return finish("pp_selftest_math memset");
+  if (n == 0) return PP_OK;
+  k_selftest_math<<<grid_for(n), kB, 0, (cudaStream_t)stream>>>(
+      n, (unsigned long long)seed, (unsigned long long *)counts_dev);
+  return finish("k_selftest_math");
 }
 
 int pp_closest_waypoint_batch(const double *x, const double *y, const double *maps_x,

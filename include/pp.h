@@ -257,6 +257,13 @@ int pp_get_xy_batch(const double *s, const double *d, const double *maps_s,
                     const double *maps_x, const double *maps_y, int32_t n_wp, double *out_x,
                     double *out_y, int64_t n, void *cuda_stream);
 
+/* Device self-test of the exact-arithmetic helpers the kernels use in place of
+ * generic divisions / fmod / atan2 (Markstein quotient with cached reciprocal,
+ * x/50, angle wrap, small-slope atan): n random trials; counts_dev[0..2] =
+ * number of results that differ bitwise from the generic operation (must be 0),
+ * counts_dev[3] = largest |fast atan - atan2| seen, in ulps. */
+int pp_selftest_math(int64_t n, uint64_t seed, int64_t *counts_dev, void *cuda_stream);
+
 /* ---- synthetic workload (host).  Counter-based RNG
  * keyed by (seed, frame index): any sub-range can be generated on any rank.
  * `out` holds HOST pointers (const is cast away; caller-owned). ---- */

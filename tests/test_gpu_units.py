@@ -134,3 +134,15 @@ def test_starter_frenet_helpers(pp, T, golden_units):
                                   None) == 0
     got = np.stack([ox.cpu().numpy(), oy.cpu().numpy()])
     assert np.allclose(got, g["hw_xy"], rtol=1e-12, atol=1e-9)  # atan2/cos/sin inside
+
+
+def test_exact_arithmetic_helpers_selftest(pp, T):
+    """The Markstein quotients (cached reciprocal, x/50) and the Sterbenz angle
+    wrap must be bit-identical to the generic / and fmod they replace — 2^27
+    random trials incl. extreme magnitudes — and the small-slope atan must stay
+    within 2 ulp of the library atan2."""
+    counts = T.zeros(4, dtype=T.int64, device="cuda")
+    assert pp.lib.pp_selftest_math(C.c_int64(1 << 27), C.c_uint64(12345), p(counts), None) == 0
+    c = counts.cpu().numpy()
+    assert c[0] == 0 and c[1] == 0 and c[2] == 0, c
+    assert 0 <= c[3] <= 2, c
