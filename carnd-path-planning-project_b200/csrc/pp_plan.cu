@@ -36,6 +36,17 @@ namespace {
 using namespace ppd;
 
 constexpr int kBlock = 128;
+// minimum resident blocks per SM the compiler must allow for (register budget);
+// tuned with ncu, see profiles/
+#ifndef PP_PREP_MINB
+#define PP_PREP_MINB 1
+#endif
+#ifndef PP_CARS_MINB
+#define PP_CARS_MINB 1
+#endif
+#ifndef PP_PLAN_MINB
+#define PP_PLAN_MINB 1
+#endif
 
 // ---------------------------------------------------------------------------
 // Stage A+B: ego state and reference segment (one frame).
@@ -324,7 +335,7 @@ Scratch carve_scratch(char *base, int64_t n, int mc) {
 }
 
 // `in` / `out` already point at the first frame of the chunk.
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, PP_PREP_MINB)
 k_prep(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
        const __grid_constant__ pp_frames in, const __grid_constant__ Scratch sc, int64_t n) {
   extern __shared__ double s_map[];
@@ -350,7 +361,7 @@ k_prep(const double *__restrict__ map_table, int n_wp, const __grid_constant__ p
   }
 }
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, PP_CARS_MINB)
 k_cars(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_frames in,
        const __grid_constant__ pp_plans out, const __grid_constant__ Scratch sc, int64_t n) {
   extern __shared__ double s_map[];
@@ -378,7 +389,7 @@ k_cars(const double *__restrict__ map_table, int n_wp, const __grid_constant__ p
   }
 }
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, PP_PLAN_MINB)
 k_plan(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
        const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
        const __grid_constant__ Scratch sc, int64_t n) {
