@@ -33,6 +33,7 @@ EXPORTS = [
     "pp_init_reference_waypoint_batch", "pp_lane_matching_batch", "pp_get_lane_pos_batch",
     "pp_spline_batch", "pp_closest_waypoint_batch", "pp_next_waypoint_batch",
     "pp_get_frenet_batch", "pp_get_xy_batch", "pp_synth_frames", "pp_selftest_math",
+    "pp_lane_change_batch", "pp_limit_speed_batch", "pp_trajectory_build_batch",
 ]
 
 

@@ -116,6 +116,79 @@ __global__ void k_get_xy(const double *s, const double *d, const double *ms, con
   if (i < n) get_xy(s[i], d[i], ms, mx, my, nwp, ox[i], oy[i]);
 }
 
+__global__ void k_lane_change(const __grid_constant__ pp_config cfg, const int32_t *car_id,
+                              const double *car_s, const double *car_vs, const int32_t *car_lane,
+                              int nc, const int32_t *ego_lane, const int32_t *target_lane,
+                              const double *ego_s, const double *ego_vs, const double *dt0,
+                              int32_t *out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  LaneStats ls;
+  lane_stats_init(ls, cfg);
+  uint32_t flags = 0;
+  for (int j = 0; j < nc; j++) {
+    const int lane = car_lane[i * nc + j];
+    if (lane < 0 || lane > 2) continue;
+    lane_stats_add(ls, cfg, car_id[i * nc + j], lane, car_s[i * nc + j], car_vs[i * nc + j],
+                   ego_lane[i], target_lane[i], ego_s[i], ego_vs[i], dt0[i], flags);
+  }
+  out[i] = lane_stats_decide(ls, cfg, ego_lane[i], target_lane[i]);
+}
+
+__global__ void k_limit_speed(const __grid_constant__ pp_config cfg, const double *car_vx,
+                              const double *car_vy, const double *next_s, const double *ego_s,
+                              const double *ego_speed, const double *ego_acc,
+                              const int32_t *in_lane, double *ls_speed, double *ls_time,
+                              double *sc_speed_o, double *sc_time_o, uint32_t *flags_o, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t flags = 0;
+  double ts, tt;
+  limit_speed(cfg, car_vx[i], car_vy[i], next_s[i], ego_s[i], ego_speed[i], ego_acc[i],
+              in_lane[i] != 0, ts, tt, flags);
+  SpeedCtl sc;
+  sc_init(sc, cfg, ego_speed[i]);
+  sc_limit(sc, ts, tt);
+  ls_speed[i] = ts;
+  ls_time[i] = tt;
+  sc_speed_o[i] = sc.target;
+  sc_time_o[i] = sc.time;
+  flags_o[i] = flags;
+}
+
+__global__ void k_trajectory(const double *table, int n_wp, const __grid_constant__ pp_config cfg,
+                             const int32_t *prev_n, const double *prev_x, const double *prev_y,
+                             const double *ego_x, const double *ego_y, const double *yaw,
+                             const int32_t *target_lane, const double *ego_d, const double *ego_vd,
+                             const double *sc_start, const double *sc_target,
+                             const double *sc_time, double *out_x, double *out_y, int32_t *out_n,
+                             uint32_t *out_flags, int64_t n) {
+  extern __shared__ double s_map[];
+  const MapView m = stage_map(s_map, table, n_wp);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int nprev = prev_n[i] >= PP_PREV_KEEP ? PP_PREV_KEEP : 0;
+  const double rx = nprev ? prev_x[i * PP_PREV_KEEP + PP_PREV_KEEP - 1] : ego_x[i];
+  const double ry = nprev ? prev_y[i * PP_PREV_KEEP + PP_PREV_KEEP - 1] : ego_y[i];
+  RefState rs;
+  init_reference(m, rx, ry, rs);
+  SpeedCtl sc;
+  sc.shift = 0;
+  sc.start = sc_start[i];
+  sc.target = sc_target[i];
+  sc.time = sc_time[i];
+  uint32_t flags = 0;
+  const int np = build_trajectory(m, cfg, rs, prev_x + i * PP_PREV_KEEP, prev_y + i * PP_PREV_KEEP,
+                                  nprev, rx, ry, yaw[i], target_lane[i], ego_d[i], ego_vd[i], sc,
+                                  out_x + i * PP_PATH_LEN, out_y + i * PP_PATH_LEN, flags);
+  for (int k = np; k < PP_PATH_LEN; k++) {
+    out_x[i * PP_PATH_LEN + k] = __longlong_as_double(0x7ff8000000000000ll);
+    out_y[i * PP_PATH_LEN + k] = __longlong_as_double(0x7ff8000000000000ll);
+  }
+  out_n[i] = np;
+  out_flags[i] = flags;
+}
+
 // Self-test of the exact-arithmetic helpers of pp_device.cuh against the generic
 // operations they replace: counts[0] div_by != a/b, counts[1] div50 != a/50,
 // counts[2] fmod_near != fmod, counts[3] max |atan2_step - atan2| in ulps.
@@ -251,6 +324,58 @@ int pp_spline_batch(const double *kx, const double *ky, int32_t n_knots, const d
   k_spline<<<grid_for(n_splines), kB, 0, (cudaStream_t)stream>>>(kx, ky, n_knots, q, n_q, out,
                                                                  n_splines);
   return finish("k_spline");
+}
+
+int pp_lane_change_batch(const pp_config *cfg, const int32_t *car_id, const double *car_s,
+                         const double *car_vs, const int32_t *car_lane, int32_t n_cars,
+                         const int32_t *ego_lane, const int32_t *target_lane, const double *ego_s,
+                         const double *ego_vs, const double *dt0, int32_t *out_target_lane,
+                         int64_t n, void *stream) {
+  if (!cfg || !ego_lane || !target_lane || !ego_s || !ego_vs || !dt0 || !out_target_lane || n < 0 ||
+      n_cars < 0)
+    return PP_E_ARG;
+  if (n_cars > 0 && (!car_id || !car_s || !car_vs || !car_lane)) return PP_E_ARG;
+  if (n == 0) return PP_OK;
+  k_lane_change<<<grid_for(n), kB, 0, (cudaStream_t)stream>>>(*cfg, car_id, car_s, car_vs, car_lane,
+                                                              n_cars, ego_lane, target_lane, ego_s,
+                                                              ego_vs, dt0, out_target_lane, n);
+  return finish("k_lane_change");
+}
+
+int pp_limit_speed_batch(const pp_config *cfg, const double *car_vx, const double *car_vy,
+                         const double *next_s, const double *ego_s, const double *ego_speed,
+                         const double *ego_acc, const int32_t *in_lane, double *out_ls_speed,
+                         double *out_ls_time, double *out_sc_speed, double *out_sc_time,
+                         uint32_t *out_flags, int64_t n, void *stream) {
+  if (!cfg || !car_vx || !car_vy || !next_s || !ego_s || !ego_speed || !ego_acc || !in_lane ||
+      !out_ls_speed || !out_ls_time || !out_sc_speed || !out_sc_time || !out_flags || n < 0)
+    return PP_E_ARG;
+  if (n == 0) return PP_OK;
+  k_limit_speed<<<grid_for(n), kB, 0, (cudaStream_t)stream>>>(
+      *cfg, car_vx, car_vy, next_s, ego_s, ego_speed, ego_acc, in_lane, out_ls_speed, out_ls_time,
+      out_sc_speed, out_sc_time, out_flags, n);
+  return finish("k_limit_speed");
+}
+
+int pp_trajectory_build_batch(const pp_map *map, const pp_config *cfg, const int32_t *prev_n,
+                              const double *prev_x, const double *prev_y, const double *ego_x,
+                              const double *ego_y, const double *ego_yaw_deg,
+                              const int32_t *target_lane, const double *ego_d,
+                              const double *ego_vd, const double *sc_start,
+                              const double *sc_target, const double *sc_time, double *out_x,
+                              double *out_y, int32_t *out_n, uint32_t *out_flags, int64_t n,
+                              void *stream) {
+  int rc = need_map(map, "pp_trajectory_build_batch");
+  if (rc != PP_OK) return rc;
+  if (!cfg || !prev_n || !prev_x || !prev_y || !ego_x || !ego_y || !ego_yaw_deg || !target_lane ||
+      !ego_d || !ego_vd || !sc_start || !sc_target || !sc_time || !out_x || !out_y || !out_n ||
+      !out_flags || n < 0)
+    return PP_E_ARG;
+  if (n == 0) return PP_OK;
+  k_trajectory<<<grid_for(n), kB, map_smem(map), (cudaStream_t)stream>>>(
+      map->dev_table, map->n, *cfg, prev_n, prev_x, prev_y, ego_x, ego_y, ego_yaw_deg, target_lane,
+      ego_d, ego_vd, sc_start, sc_target, sc_time, out_x, out_y, out_n, out_flags, n);
+  return finish("k_trajectory");
 }
 
 int pp_selftest_math(int64_t n, uint64_t seed, int64_t *counts_dev, void *stream) {

@@ -257,6 +257,39 @@ int pp_get_xy_batch(const double *s, const double *d, const double *maps_s,
                     const double *maps_x, const double *maps_y, int32_t n_wp, double *out_x,
                     double *out_y, int64_t n, void *cuda_stream);
 
+/* LaneChangePlanner::calculate_target_lane (src/main.cpp:364-485) on explicit,
+ * already matched cars: problem i has n_cars cars car_*[i*n_cars + j] (lane < 0
+ * = car not in the map) and scalars ego_lane/target_lane/ego_s/ego_vs/dt0 [n].
+ * out_target_lane[n]. */
+int pp_lane_change_batch(const pp_config *cfg, const int32_t *car_id, const double *car_s,
+                         const double *car_vs, const int32_t *car_lane, int32_t n_cars,
+                         const int32_t *ego_lane, const int32_t *target_lane, const double *ego_s,
+                         const double *ego_vs, const double *dt0, int32_t *out_target_lane,
+                         int64_t n, void *cuda_stream);
+
+/* LimitSpeed::calculate (src/main.cpp:1068-1150) for one followed car per
+ * element, then SpeedController(ego_speed).add_limit_breakpoint (:495-533):
+ * out_ls_* = the LimitSpeed result, out_sc_* = the controller's target after
+ * the limit, out_flags = PP_F_COLLISION|BRAKE|MAXBRAKE|ADJUST|KEEP. */
+int pp_limit_speed_batch(const pp_config *cfg, const double *car_vx, const double *car_vy,
+                         const double *next_s, const double *ego_s, const double *ego_speed,
+                         const double *ego_acc, const int32_t *in_lane, double *out_ls_speed,
+                         double *out_ls_time, double *out_sc_speed, double *out_sc_time,
+                         uint32_t *out_flags, int64_t n, void *cuda_stream);
+
+/* TrajectoryBuilder::build (src/main.cpp:565-1049) on explicit inputs: the ego
+ * reference point is the last previous point (or ego_x/ego_y when prev_n < 10),
+ * sc_* is the SpeedController state handed to build().  prev_x/prev_y [n][10],
+ * out_x/out_y [n][50] (NaN beyond out_n), out_flags [n]. */
+int pp_trajectory_build_batch(const pp_map *map, const pp_config *cfg, const int32_t *prev_n,
+                              const double *prev_x, const double *prev_y, const double *ego_x,
+                              const double *ego_y, const double *ego_yaw_deg,
+                              const int32_t *target_lane, const double *ego_d,
+                              const double *ego_vd, const double *sc_start,
+                              const double *sc_target, const double *sc_time, double *out_x,
+                              double *out_y, int32_t *out_n, uint32_t *out_flags, int64_t n,
+                              void *cuda_stream);
+
 /* Device self-test of the exact-arithmetic helpers the kernels use in place of
  * generic divisions / fmod / atan2 (Markstein quotient with cached reciprocal,
  * x/50, angle wrap, small-slope atan): n random trials; counts_dev[0..2] =

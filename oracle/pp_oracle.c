@@ -1218,3 +1218,34 @@ void ppo_limit_speed(const double *car_vx, const double *car_vy, const double *n
     flags[i] = fl & (PP_F_COLLISION | PP_F_BRAKE | PP_F_MAXBRAKE | PP_F_ADJUST | PP_F_KEEP);
   }
 }
+
+/* TrajectoryBuilder::build on explicit inputs (the reference point is the last
+ * kept previous point, or the telemetry pose on a cold start). */
+void ppo_trajectory_build(ppo_map *m, const int32_t *prev_n, const double *prev_x,
+                          const double *prev_y, const double *ego_x, const double *ego_y,
+                          const double *yaw, const int32_t *target_lane, const double *ego_d,
+                          const double *ego_vd, const double *sc_start, const double *sc_target,
+                          const double *sc_time, double *out_x, double *out_y, int32_t *out_n,
+                          uint32_t *out_flags, int64_t n) {
+  const int K = PP_PREV_KEEP;
+  for (int64_t i = 0; i < n; i++) {
+    vec2 prev[PP_PREV_KEEP];
+    int nprev = prev_n[i] >= K ? K : 0;
+    for (int k = 0; k < K; k++) {
+      prev[k].x = prev_x[i * K + k];
+      prev[k].y = prev_y[i * K + k];
+    }
+    double rx = nprev ? prev[K - 1].x : ego_x[i], ry = nprev ? prev[K - 1].y : ego_y[i];
+    refstate rs;
+    init_reference(m, rx, ry, &rs);
+    speedctl sc;
+    sc.shift = 0;
+    sc.start = sc_start[i];
+    sc.target = sc_target[i];
+    sc.time = sc_time[i];
+    uint32_t fl = 0;
+    out_n[i] = build_trajectory(m, &rs, prev, nprev, rx, ry, yaw[i], target_lane[i], ego_d[i],
+                                ego_vd[i], &sc, out_x + i * PP_PATH_LEN, out_y + i * PP_PATH_LEN, &fl);
+    out_flags[i] = fl;
+  }
+}

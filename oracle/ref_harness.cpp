@@ -500,6 +500,39 @@ void ppref_limit_speed(const double *car_vx, const double *car_vy, const double 
   fLog = NULL;
 }
 
+// TrajectoryBuilder::build on explicit inputs.
+void ppref_trajectory_build(ppref_map *m, const int32_t *prev_n, const double *prev_x,
+                            const double *prev_y, const double *ego_x, const double *ego_y,
+                            const double *yaw, const int32_t *target_lane, const double *ego_d,
+                            const double *ego_vd, const double *sc_start, const double *sc_target,
+                            const double *sc_time, double *out_x, double *out_y, int32_t *out_n,
+                            uint32_t *out_flags, int64_t n) {
+  Map map = m->map;
+  fLog = devnull();
+  const int K = PP_PREV_KEEP;
+  for (int64_t i = 0; i < n; i++) {
+    t_flags = 0;
+    vector<Point> prev;
+    if (prev_n[i] >= K)
+      for (int k = 0; k < K; k++) prev.push_back(Point(prev_x[i * K + k], prev_y[i * K + k]));
+    double rx = prev.empty() ? ego_x[i] : prev[K - 1].x;
+    double ry = prev.empty() ? ego_y[i] : prev[K - 1].y;
+    map.init_reference_waypoint(rx, ry);
+    SpeedController sc(sc_start[i]);
+    sc.target_speed = sc_target[i];
+    sc.target_time = sc_time[i];
+    TrajectoryBuilder tb;
+    vector<Point> tr = tb.build(prev, rx, ry, yaw[i], 0, target_lane[i], ego_d[i], ego_vd[i], map, sc);
+    out_n[i] = (int32_t)tr.size();
+    for (size_t k = 0; k < tr.size() && k < PP_PATH_LEN; k++) {
+      out_x[i * PP_PATH_LEN + k] = tr[k].x;
+      out_y[i * PP_PATH_LEN + k] = tr[k].y;
+    }
+    out_flags[i] = t_flags;
+  }
+  fLog = NULL;
+}
+
 // ---------------------------------------------------------------------------
 // lambda harness: drive the untouched onMessage lambda.
 // ---------------------------------------------------------------------------

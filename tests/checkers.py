@@ -213,6 +213,21 @@ class Checker:
         return dict(ls_speed=outs[0], ls_time=outs[1], sc_speed=outs[2], sc_time=outs[3],
                     flags=flags)
 
+    def trajectory_build(self, prev_n, prev_x, prev_y, ego_x, ego_y, yaw, target_lane, ego_d,
+                         ego_vd, sc_start, sc_target, sc_time):
+        prev_n, target_lane = _i32(prev_n), _i32(target_lane)
+        f = [_f64(v) for v in (prev_x, prev_y, ego_x, ego_y, yaw)]
+        g = [_f64(v) for v in (ego_d, ego_vd, sc_start, sc_target, sc_time)]
+        n = len(prev_n)
+        ox = np.full((n, abi.PATH_LEN), np.nan)
+        oy = np.full((n, abi.PATH_LEN), np.nan)
+        on = np.zeros(n, np.int32)
+        fl = np.zeros(n, np.uint32)
+        self._fn("trajectory_build")(self.map, _p(prev_n), *[_p(v) for v in f], _p(target_lane),
+                                     *[_p(v) for v in g], _p(ox), _p(oy), _p(on), _p(fl),
+                                     C.c_int64(n))
+        return ox, oy, on, fl
+
     def lambda_sequence(self, frames):
         """ref only: the untouched onMessage lambda over a frame SEQUENCE."""
         assert self.kind == "ref"

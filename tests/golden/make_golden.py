@@ -154,6 +154,20 @@ def units():
     ls = ref.limit_speed(cvx, cvy, nxs, np.zeros(n), espd, eacc, inl)
     for k, v in ls.items():
         blob["ls_" + k] = v
+    # TrajectoryBuilder::build on explicit inputs: take real frames for plausible geometry
+    fbt = pp.synth_frames(m, 384, 12, seed=424242, rare_permille=200)
+    pl = ref.plan(fbt, want_flags=False)
+    tl = np.clip(pl.ego_lane + rng.integers(-1, 2, fbt.n), 0, 2).astype(np.int32)
+    sc_target = rng.uniform(0.0, 22.2, fbt.n)
+    sc_time = rng.uniform(0.3, 4.0, fbt.n)
+    blob["tr_prev_n"], blob["tr_prev_x"], blob["tr_prev_y"] = fbt.prev_n, fbt.prev_x, fbt.prev_y
+    blob["tr_ego"] = np.stack([fbt.ego_x, fbt.ego_y, fbt.ego_yaw_deg, pl.ego_d, pl.ego_vd,
+                               pl.ego_speed, sc_target, sc_time])
+    blob["tr_tl"] = tl
+    tx, ty, tn, tf = ref.trajectory_build(fbt.prev_n, fbt.prev_x, fbt.prev_y, fbt.ego_x, fbt.ego_y,
+                                          fbt.ego_yaw_deg, tl, pl.ego_d, pl.ego_vd, pl.ego_speed,
+                                          sc_target, sc_time)
+    blob["tr_x"], blob["tr_y"], blob["tr_n"], blob["tr_flags"] = tx, ty, tn, tf
     np.savez_compressed(os.path.join(HERE, "units.npz"), **blob)
     print("units.npz", len(blob), "arrays")
 

@@ -136,6 +136,69 @@ def test_starter_frenet_helpers(pp, T, golden_units):
     assert np.allclose(got, g["hw_xy"], rtol=1e-12, atol=1e-9)  # atan2/cos/sin inside
 
 
+def test_lane_change_planner(pp, T, golden_units):
+    """LaneChangePlanner::calculate_target_lane (src/main.cpp:364-485), bit-exact,
+    incl. ties between two cars (lowest id wins) and all three target lanes."""
+    g = golden_units
+    cs, cvs = g["lc_cars"]
+    es, evs, dt0 = g["lc_ego"]
+    n, nc = g["lc_id"].shape
+    cfg = pp.default_config()
+    out = out_i32(T, n)
+    args = [dev(T, g["lc_id"], np.int32), dev(T, cs), dev(T, cvs), dev(T, g["lc_lane"], np.int32)]
+    sc = [dev(T, g["lc_el"], np.int32), dev(T, g["lc_tl"], np.int32), dev(T, es), dev(T, evs),
+          dev(T, dt0)]
+    assert pp.lib.pp_lane_change_batch(C.byref(cfg), *[p(t) for t in args], nc, *[p(t) for t in sc],
+                                       p(out), C.c_int64(n), None) == 0
+    assert np.array_equal(out.cpu().numpy(), g["lc_out"])
+    # car order must not matter
+    perm = np.random.default_rng(1).permutation(nc)
+    args = [dev(T, g["lc_id"][:, perm], np.int32), dev(T, cs[:, perm]), dev(T, cvs[:, perm]),
+            dev(T, g["lc_lane"][:, perm], np.int32)]
+    assert pp.lib.pp_lane_change_batch(C.byref(cfg), *[p(t) for t in args], nc, *[p(t) for t in sc],
+                                       p(out), C.c_int64(n), None) == 0
+    assert np.array_equal(out.cpu().numpy(), g["lc_out"])
+
+
+def test_limit_speed_and_speed_controller(pp, T, golden_units):
+    """LimitSpeed::calculate + SpeedController::add_limit_breakpoint, bit-exact."""
+    g = golden_units
+    ins = [dev(T, a) for a in g["ls_in"]]
+    inl = dev(T, g["ls_inlane"], np.int32)
+    n = inl.numel()
+    outs = [out_f64(T, n) for _ in range(4)]
+    fl = out_i32(T, n)
+    cfg = pp.default_config()
+    assert pp.lib.pp_limit_speed_batch(C.byref(cfg), *[p(t) for t in ins], p(inl),
+                                       *[p(t) for t in outs], p(fl), C.c_int64(n), None) == 0
+    for o, k in zip(outs, ("ls_speed", "ls_time", "sc_speed", "sc_time")):
+        assert np.array_equal(o.cpu().numpy(), g["ls_" + k]), k
+    assert np.array_equal(fl.cpu().numpy().view(np.uint32), g["ls_flags"])
+    for name in ("COLLISION", "BRAKE", "MAXBRAKE", "ADJUST", "KEEP"):
+        assert (g["ls_flags"] & pp.FLAG[name]).any(), name
+
+
+def test_trajectory_builder(pp, T, gmap, golden_units):
+    """TrajectoryBuilder::build on explicit inputs vs the reference's own class:
+    point counts identical, points within 1e-9 rel / 1e-6 m."""
+    g = golden_units
+    ex, ey, yaw, ed, evd, start, target, time = g["tr_ego"]
+    n = len(ex)
+    cfg = pp.default_config()
+    ox, oy = out_f64(T, n, 50), out_f64(T, n, 50)
+    on, fl = out_i32(T, n), out_i32(T, n)
+    a = [dev(T, g["tr_prev_n"], np.int32), dev(T, g["tr_prev_x"]), dev(T, g["tr_prev_y"]), dev(T, ex),
+         dev(T, ey), dev(T, yaw), dev(T, g["tr_tl"], np.int32), dev(T, ed), dev(T, evd), dev(T, start),
+         dev(T, target), dev(T, time)]
+    assert pp.lib.pp_trajectory_build_batch(gmap.handle, C.byref(cfg), *[p(t) for t in a], p(ox),
+                                            p(oy), p(on), p(fl), C.c_int64(n), None) == 0
+    assert np.array_equal(on.cpu().numpy(), g["tr_n"])
+    for got, want in ((ox.cpu().numpy(), g["tr_x"]), (oy.cpu().numpy(), g["tr_y"])):
+        assert np.array_equal(got != got, want != want)
+        err = np.nanmax(np.abs(got - want))
+        assert err <= 1e-6 and np.nanmax(np.abs(got - want) / np.abs(want)) <= 1e-9, err
+
+
 def test_exact_arithmetic_helpers_selftest(pp, T):
     """The Markstein quotients (cached reciprocal, x/50) and the Sterbenz angle
     wrap must be bit-identical to the generic / and fmod they replace — 2^27

@@ -121,6 +121,22 @@ def test_oracle_units_match_golden(oracle, golden_units):
         assert np.array_equal(v, g["ls_" + k]), k
 
 
+def test_oracle_trajectory_builder_matches_golden(oracle, golden_units):
+    g = golden_units
+    ex, ey, yaw, ed, evd, start, target, time = g["tr_ego"]
+    ox, oy, on, fl = oracle.trajectory_build(g["tr_prev_n"], g["tr_prev_x"], g["tr_prev_y"], ex, ey,
+                                             yaw, g["tr_tl"], ed, evd, start, target, time)
+    assert np.array_equal(on, g["tr_n"])
+    assert np.array_equal(ox, g["tr_x"], equal_nan=True) and np.array_equal(oy, g["tr_y"], equal_nan=True)
+    mask = 0
+    for k in ("SPLINE_INPUT_ERR", "ACC_OVERRIDE", "CURV_ADJUST", "ACCT_HIGH", "ACCN_HIGH"):
+        mask |= 1 << ["EGO_MATCH_FAIL", "CAR_DROPPED", "COLLISION", "BRAKE", "MAXBRAKE", "ADJUST", "KEEP",
+                      "SPLINE_INPUT_ERR", "FALLBACK", "ACC_OVERRIDE", "CURV_ADJUST", "LANE_SWITCH_NEG",
+                      "VETO", "ACCT_HIGH", "ACCN_HIGH"].index(k)
+    assert np.array_equal(fl & mask, g["tr_flags"] & mask)
+    assert (g["tr_flags"] & (1 << 10)).any() and (g["tr_flags"] & (1 << 9)).any()  # both limiters exercised
+
+
 def test_oracle_starter_helpers_match_golden(oracle, golden_units, pp):
     g = golden_units
     csv = np.loadtxt(pp.MAP_CSV)
