@@ -34,6 +34,7 @@ EXPORTS = [
     "pp_spline_batch", "pp_closest_waypoint_batch", "pp_next_waypoint_batch",
     "pp_get_frenet_batch", "pp_get_xy_batch", "pp_synth_frames", "pp_selftest_math",
     "pp_lane_change_batch", "pp_limit_speed_batch", "pp_trajectory_build_batch",
+    "pp_set_phase_timing", "pp_get_phase_ms",
 ]
 
 
@@ -73,6 +74,18 @@ def device_count() -> int:
 
 def set_kernel_variant(v: int):
     _check(lib.pp_set_kernel_variant(C.c_int(v)), "pp_set_kernel_variant")
+
+
+def set_phase_timing(on: bool):
+    _check(lib.pp_set_phase_timing(C.c_int(1 if on else 0)), "pp_set_phase_timing")
+
+
+def get_phase_ms():
+    """(ms[3] = prep, cars, plan summed over the chunks since the last call, chunks)."""
+    ms = (C.c_double * 3)()
+    chunks = C.c_int64(0)
+    _check(lib.pp_get_phase_ms(ms, C.byref(chunks)), "pp_get_phase_ms")
+    return [float(v) for v in ms], int(chunks.value)
 
 
 def _ptr(t):

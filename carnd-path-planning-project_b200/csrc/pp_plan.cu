@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <vector>
 
 #include "pp_device.cuh"
 #include "pp_internal.h"
@@ -469,6 +470,34 @@ stats_kernel(const __grid_constant__ pp_plans p, int64_t n, unsigned long long *
 int g_variant = 0;
 int g_sm_count = 0;
 
+// ---- optional per-phase timing (bench.py / profiles): CUDA events recorded on
+// the caller's stream around every kernel of the pipeline.
+constexpr int kPhases = 3;  // prep, cars, plan
+constexpr int kMaxTimedChunks = 4096;
+bool g_phase_timing = false;
+struct PhaseEvents {
+  cudaEvent_t ev[kPhases + 1];
+};
+std::vector<PhaseEvents> g_phase_events;  // one entry per chunk launched since the last read
+std::vector<PhaseEvents> g_phase_pool;    // recycled events
+
+void phase_mark(PhaseEvents *pe, int i, cudaStream_t st) {
+  if (pe) cudaEventRecord(pe->ev[i], st);
+}
+PhaseEvents *phase_begin() {
+  if (!g_phase_timing || (int)g_phase_events.size() >= kMaxTimedChunks) return nullptr;
+  PhaseEvents pe;
+  if (!g_phase_pool.empty()) {
+    pe = g_phase_pool.back();
+    g_phase_pool.pop_back();
+  } else {
+    for (int i = 0; i <= kPhases; i++)
+      if (cudaEventCreate(&pe.ev[i]) != cudaSuccess) return nullptr;
+  }
+  g_phase_events.push_back(pe);
+  return &g_phase_events.back();
+}
+
 int sm_count() {
   if (g_sm_count == 0) {
     int dev = 0;
@@ -634,16 +663,47 @@ extern "C" int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_f
     const int64_t cnt = (n_frames - lo) < chunk ? (n_frames - lo) : chunk;
     const pp_frames fin = offset_frames(*in, lo);
     const pp_plans fout = offset_plans(*out, lo, mc);
+    PhaseEvents *pe = phase_begin();
+    phase_mark(pe, 0, st);
     k_prep<<<grid_for(cnt, 12), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, fin, sc, cnt);
+    phase_mark(pe, 1, st);
     if (mc > 0)
       k_cars<<<grid_for(cnt * mc, 12), kBlock, smem, st>>>(map->dev_table, map->n, fin, fout, sc,
                                                            cnt);
+    phase_mark(pe, 2, st);
     k_plan<<<grid_for(cnt, 12), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, fin, fout, sc,
                                                     cnt);
+    phase_mark(pe, 3, st);
     ppi::count_launch(mc > 0 ? 3 : 2);
     rc = check_launch("plan pipeline");
   }
   cudaFreeAsync(buf, st);
+  return rc;
+}
+
+extern "C" int pp_set_phase_timing(int on) {
+  g_phase_timing = on != 0;
+  return PP_OK;
+}
+
+// Sums the per-phase device times (ms) of every pipeline chunk launched since
+// the previous call while phase timing was on; synchronises on the last event.
+extern "C" int pp_get_phase_ms(double *ms_out, int64_t *chunks_out) {
+  if (!ms_out) return PP_E_ARG;
+  for (int i = 0; i < kPhases; i++) ms_out[i] = 0;
+  int rc = PP_OK;
+  for (PhaseEvents &pe : g_phase_events) {
+    if (cudaEventSynchronize(pe.ev[kPhases]) != cudaSuccess) rc = PP_E_CUDA;
+    for (int i = 0; i < kPhases && rc == PP_OK; i++) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, pe.ev[i], pe.ev[i + 1]) != cudaSuccess) rc = PP_E_CUDA;
+      ms_out[i] += ms;
+    }
+    g_phase_pool.push_back(pe);
+  }
+  if (chunks_out) *chunks_out = (int64_t)g_phase_events.size();
+  g_phase_events.clear();
+  if (rc != PP_OK) check_launch("pp_get_phase_ms");
   return rc;
 }
 

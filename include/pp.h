@@ -196,9 +196,16 @@ int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const pp_frames 
 int pp_stats_batch(const pp_plans *plans_dev, int64_t n_frames, int64_t *stats_dev,
                    void *cuda_stream);
 
-/* Kernel selection for pp_plan_batch: 0 = auto, 1 = one thread per frame
- * (throughput mapping), 2 = one warp per frame (latency mapping). */
+/* Kernel selection for pp_plan_batch: 0 = auto (pipeline; the fused kernel for
+ * batches under 4096 frames), 1 = fused single kernel, 2 = pipeline. */
 int pp_set_kernel_variant(int variant);
+/* Measurement aid (bench.py): when on, pp_plan_batch records CUDA events on the
+ * caller's stream around each kernel of the pipeline.  pp_get_phase_ms waits for
+ * the last of them and returns the summed device time in ms of ms_out[0] = ego
+ * preparation, [1] = per-car matching, [2] = decision + trajectory over all
+ * chunks launched since the previous call (chunks_out, may be NULL). */
+int pp_set_phase_timing(int on);
+int pp_get_phase_ms(double *ms_out, int64_t *chunks_out);
 /* Number of kernel launches issued by this library since load (bench.py's
  * gpu_launches). */
 int64_t pp_launch_count(void);
