@@ -81,8 +81,8 @@ def set_phase_timing(on: bool):
 
 
 def get_phase_ms():
-    """(ms[3] = prep, cars, plan summed over the chunks since the last call, chunks)."""
-    ms = (C.c_double * 3)()
+    """(ms[5] = prep, cars, decide, emit, slow summed over the chunks since the last call, chunks)."""
+    ms = (C.c_double * 5)()
     chunks = C.c_int64(0)
     _check(lib.pp_get_phase_ms(ms, C.byref(chunks)), "pp_get_phase_ms")
     return [float(v) for v in ms], int(chunks.value)

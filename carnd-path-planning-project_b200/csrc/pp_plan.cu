@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "pp_device.cuh"
@@ -186,9 +187,17 @@ PPD_INLINE void behav_add(Behav &b, const pp_config &cfg, const FrameCtx &c, int
 // ---------------------------------------------------------------------------
 // Stage D..I tail: decision, speed target, trajectory, outputs (one frame).
 // ---------------------------------------------------------------------------
-PPD_INLINE void stage_finish(const MapView &m, const pp_config &cfg, const pp_frames &in,
-                             const pp_plans &out, int64_t f, const FrameCtx &c, const Behav &b,
-                             int tl_in, uint32_t flags) {
+struct Decision {
+  int target_lane;
+  SpeedCtl sc;
+  uint32_t flags;
+};
+
+// lane decision, followed cars, speed target; writes every per-frame output
+// except the trajectory itself, n_points and flags.
+PPD_INLINE Decision stage_decide(const pp_config &cfg, const pp_frames &in, const pp_plans &out,
+                                 int64_t f, const FrameCtx &c, const Behav &b, int tl_in,
+                                 uint32_t flags) {
   const int64_t cb = f * in.max_cars;
   // lane decision (:1355) + veto (:1358-1369)
   int target_lane = lane_stats_decide(b.ls, cfg, c.lane, tl_in);
@@ -220,21 +229,9 @@ PPD_INLINE void stage_finish(const MapView &m, const pp_config &cfg, const pp_fr
   }
   if (out.target_speed) out.target_speed[f] = sc.target;
   if (out.target_time) out.target_time[f] = sc.time;
-
-  // trajectory (:1446-1448)
-  const int np = build_trajectory(m, cfg, c.rs, in.prev_x + f * PP_PREV_KEEP,
-                                  in.prev_y + f * PP_PREV_KEEP, c.nprev, c.x, c.y,
-                                  in.ego_yaw_deg[f], target_lane, c.d, c.vd, sc,
-                                  out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN, flags);
-  for (int i = np; i < PP_PATH_LEN; i++) {  // short (fallback) paths: pad with NaN
-    out.next_x[f * PP_PATH_LEN + i] = __longlong_as_double(0x7ff8000000000000ll);
-    out.next_y[f * PP_PATH_LEN + i] = __longlong_as_double(0x7ff8000000000000ll);
-  }
-  out.n_points[f] = np;
   out.ego_lane[f] = c.lane;
   out.ref_wp[f] = c.rs.wp;
   out.target_lane[f] = target_lane;
-  out.flags[f] = flags;
   if (out.ego_s) out.ego_s[f] = c.s;
   if (out.ego_d) out.ego_d[f] = c.d;
   if (out.ego_vs) out.ego_vs[f] = c.vs;
@@ -243,6 +240,36 @@ PPD_INLINE void stage_finish(const MapView &m, const pp_config &cfg, const pp_fr
   if (out.ego_acc) out.ego_acc[f] = c.acc;
   if (out.next_car_id) out.next_car_id[f] = b.own.id;
   if (out.next_car_in_target_lane) out.next_car_in_target_lane[f] = tl.id;
+  Decision d;
+  d.target_lane = target_lane;
+  d.sc = sc;
+  d.flags = flags;
+  return d;
+}
+
+PPD_INLINE void store_path_tail(const pp_plans &out, int64_t f, int np, uint32_t flags) {
+  for (int i = np; i < PP_PATH_LEN; i++) {  // short (fallback) paths: pad with NaN
+    out.next_x[f * PP_PATH_LEN + i] = __longlong_as_double(0x7ff8000000000000ll);
+    out.next_y[f * PP_PATH_LEN + i] = __longlong_as_double(0x7ff8000000000000ll);
+  }
+  out.n_points[f] = np;
+  out.flags[f] = flags;
+}
+
+// ---------------------------------------------------------------------------
+// Stage D..I tail: decision, speed target, trajectory, outputs (one frame).
+// ---------------------------------------------------------------------------
+PPD_INLINE void stage_finish(const MapView &m, const pp_config &cfg, const pp_frames &in,
+                             const pp_plans &out, int64_t f, const FrameCtx &c, const Behav &b,
+                             int tl_in, uint32_t flags0) {
+  const Decision d = stage_decide(cfg, in, out, f, c, b, tl_in, flags0);
+  uint32_t flags = d.flags;
+  // trajectory (:1446-1448)
+  const int np = build_trajectory(m, cfg, c.rs, in.prev_x + f * PP_PREV_KEEP,
+                                  in.prev_y + f * PP_PREV_KEEP, c.nprev, c.x, c.y,
+                                  in.ego_yaw_deg[f], d.target_lane, c.d, c.vd, d.sc,
+                                  out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN, flags);
+  store_path_tail(out, f, np, flags);
 }
 
 PPD_INLINE void store_car(const pp_plans &out, int64_t slot, const CarRes &r) {
@@ -252,6 +279,27 @@ PPD_INLINE void store_car(const pp_plans &out, int64_t slot, const CarRes &r) {
   if (out.car_d) out.car_d[slot] = r.d;
   if (out.car_vs) out.car_vs[slot] = r.vs;
   if (out.car_vd) out.car_vd[slot] = r.vd;
+}
+
+// The whole step for one frame, from its inputs alone.
+PPD_INLINE void plan_one_frame(const MapView &m, const pp_config &cfg, const pp_frames &in,
+                               const pp_plans &out, int64_t f) {
+  const FrameCtx c = stage_prep(m, cfg, in, f);
+  uint32_t flags = c.flags;
+  const int mc = in.max_cars;
+  int nc = in.n_cars[f];
+  if (nc > mc) nc = mc;
+  const int tl_in = in.target_lane_in[f];
+  Behav b;
+  behav_init(b, cfg);
+  const int64_t cb = f * mc;
+  for (int j = 0; j < nc; j++) {
+    const CarRes r = stage_car(m, c.rs, in.car_x[cb + j], in.car_y[cb + j], in.car_vx[cb + j],
+                               in.car_vy[cb + j]);
+    store_car(out, cb + j, r);
+    behav_add(b, cfg, c, tl_in, in.car_id[cb + j], j, r, flags);
+  }
+  stage_finish(m, cfg, in, out, f, c, b, tl_in, flags);
 }
 
 // ===========================================================================
@@ -264,24 +312,8 @@ plan_fused(const double *__restrict__ map_table, int n_wp, const __grid_constant
   extern __shared__ double s_map[];
   const MapView m = stage_map(s_map, map_table, n_wp);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_frames; f += stride) {
-    const FrameCtx c = stage_prep(m, cfg, in, f);
-    uint32_t flags = c.flags;
-    const int mc = in.max_cars;
-    int nc = in.n_cars[f];
-    if (nc > mc) nc = mc;
-    const int tl_in = in.target_lane_in[f];
-    Behav b;
-    behav_init(b, cfg);
-    const int64_t cb = f * mc;
-    for (int j = 0; j < nc; j++) {
-      const CarRes r = stage_car(m, c.rs, in.car_x[cb + j], in.car_y[cb + j], in.car_vx[cb + j],
-                                 in.car_vy[cb + j]);
-      store_car(out, cb + j, r);
-      behav_add(b, cfg, c, tl_in, in.car_id[cb + j], j, r, flags);
-    }
-    stage_finish(m, cfg, in, out, f, c, b, tl_in, flags);
-  }
+  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_frames; f += stride)
+    plan_one_frame(m, cfg, in, out, f);
 }
 
 // ===========================================================================
@@ -294,13 +326,26 @@ struct Scratch {
   uint32_t *flags;
   double *car_s, *car_d, *car_vs, *car_vd;  // [n][max_cars]
   int32_t *car_lane, *car_wp;
+  // between k_decide and k_emit: SpeedController, local frame, the reachable knots
+  double *est;         // [kEstRows][n]
+  int32_t *e_np;       // points already written (kept previous points)
+  int32_t *e_nk;       // stored knots | kEstPartial; 0 = frame not for k_emit
+  uint32_t *e_flags;   // flags raised so far
+  // frames that need the complete path (k_slow): queue A is filled by k_decide, B by k_emit
+  int32_t *slow_qa, *slow_qb;
+  int32_t *slow_na, *slow_nb;
+  int32_t *dbg;  // PP_DEBUG_SLOW: bail-out reasons of k_emit, else nullptr
   int64_t n;  // frames in this chunk (stride of ratio)
 };
+constexpr int kEstHead = 7;  // sc.start, sc.target, sc.time, cx, cy, ca, sa
+constexpr int kEstRows = kEstHead + 5 * PPD_TAILK;
+constexpr int kEstPartial = 1 << 8;
+constexpr int kEstFallback = 1 << 9;  // e_nk = kEstFallback | ncp: state for k_fallback, not k_emit
 
 size_t scratch_bytes(int64_t n, int mc) {
-  const size_t per_frame = 11 * 8 + 4 * 4;
+  const size_t per_frame = 11 * 8 + 4 * 4 + (size_t)kEstRows * 8 + 3 * 4;
   const size_t per_car = 4 * 8 + 2 * 4;
-  return (size_t)n * (per_frame + (size_t)mc * per_car) + 64 * 32;
+  return (size_t)n * (per_frame + (size_t)mc * per_car) + 64 * 256;
 }
 
 Scratch carve_scratch(char *base, int64_t n, int mc) {
@@ -331,6 +376,11 @@ Scratch carve_scratch(char *base, int64_t n, int mc) {
   s.car_vd = (double *)take(NC * 8);
   s.car_lane = (int32_t *)take(NC * 4);
   s.car_wp = (int32_t *)take(NC * 4);
+  s.est = (double *)take((size_t)kEstRows * N * 8);
+  s.e_np = (int32_t *)take(N * 4);
+  s.e_nk = (int32_t *)take(N * 4);
+  s.e_flags = (uint32_t *)take(N * 4);
+  s.slow_qa = s.slow_qb = s.slow_na = s.slow_nb = s.dbg = nullptr;  // set per chunk by the caller
   s.n = n;
   return s;
 }
@@ -390,48 +440,209 @@ k_cars(const double *__restrict__ map_table, int n_wp, const __grid_constant__ p
   }
 }
 
+// Everything of a frame after the per-car phase, from the scratch of k_prep /
+// k_cars: the complete path (any frame).
+PPD_INLINE void load_ctx(const Scratch &sc, int64_t f, FrameCtx &c) {
+  c.x = sc.x[f];
+  c.y = sc.y[f];
+  c.speed = sc.speed[f];
+  c.acc = sc.acc[f];
+  c.s = sc.s[f];
+  c.d = sc.d[f];
+  c.vs = sc.vs[f];
+  c.vd = sc.vd[f];
+  c.rs.ratio[0] = sc.ratio[f];
+  c.rs.ratio[1] = sc.ratio[sc.n + f];
+  c.rs.ratio[2] = sc.ratio[2 * sc.n + f];
+  c.rs.wp = sc.wp[f];
+  c.lane = sc.lane[f];
+  c.nprev = sc.nprev[f];
+  c.flags = sc.flags[f];
+}
+PPD_INLINE void reduce_cars(const pp_config &cfg, const pp_frames &in, const Scratch &sc, int64_t f,
+                            const FrameCtx &c, int tl_in, Behav &b, uint32_t &flags) {
+  const int mc = in.max_cars;
+  int nc = in.n_cars[f];
+  if (nc > mc) nc = mc;
+  behav_init(b, cfg);
+  const int64_t cb = f * mc;
+  for (int j = 0; j < nc; j++) {
+    CarRes r;
+    r.lane = sc.car_lane[cb + j];
+    r.wp = sc.car_wp[cb + j];
+    r.s = sc.car_s[cb + j];
+    r.d = sc.car_d[cb + j];
+    r.vs = sc.car_vs[cb + j];
+    r.vd = sc.car_vd[cb + j];
+    behav_add(b, cfg, c, tl_in, in.car_id[cb + j], j, r, flags);
+  }
+}
+
+// Decision + trajectory set-up + spline fit (one thread per frame).  Frames whose
+// trajectory is the ordinary spline emission hand their state to k_emit; the
+// rest (angle-based generator, :848) go to the queue of k_slow.
 __global__ void __launch_bounds__(kBlock, PP_PLAN_MINB)
-k_plan(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
-       const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
-       const __grid_constant__ Scratch sc, int64_t n) {
+k_decide(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
+         const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
+         const __grid_constant__ Scratch sc, int64_t n) {
   extern __shared__ double s_map[];
   const MapView m = stage_map(s_map, map_table, n_wp);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += stride) {
     FrameCtx c;
-    c.x = sc.x[f];
-    c.y = sc.y[f];
-    c.speed = sc.speed[f];
-    c.acc = sc.acc[f];
-    c.s = sc.s[f];
-    c.d = sc.d[f];
-    c.vs = sc.vs[f];
-    c.vd = sc.vd[f];
-    c.rs.ratio[0] = sc.ratio[f];
-    c.rs.ratio[1] = sc.ratio[sc.n + f];
-    c.rs.ratio[2] = sc.ratio[2 * sc.n + f];
-    c.rs.wp = sc.wp[f];
-    c.lane = sc.lane[f];
-    c.nprev = sc.nprev[f];
-    c.flags = sc.flags[f];
+    load_ctx(sc, f, c);
     uint32_t flags = c.flags;
-    const int mc = in.max_cars;
-    int nc = in.n_cars[f];
-    if (nc > mc) nc = mc;
     const int tl_in = in.target_lane_in[f];
     Behav b;
-    behav_init(b, cfg);
-    const int64_t cb = f * mc;
-    for (int j = 0; j < nc; j++) {
-      CarRes r;
-      r.lane = sc.car_lane[cb + j];
-      r.wp = sc.car_wp[cb + j];
-      r.s = sc.car_s[cb + j];
-      r.d = sc.car_d[cb + j];
-      r.vs = sc.car_vs[cb + j];
-      r.vd = sc.car_vd[cb + j];
-      behav_add(b, cfg, c, tl_in, in.car_id[cb + j], j, r, flags);
+    reduce_cars(cfg, in, sc, f, c, tl_in, b, flags);
+    const Decision d = stage_decide(cfg, in, out, f, c, b, tl_in, flags);
+    flags = d.flags;
+    Spline sp;
+    TrajFrame tf;
+    traj_setup(m, cfg, c.rs, in.prev_x + f * PP_PREV_KEEP, in.prev_y + f * PP_PREV_KEEP, c.nprev,
+               c.x, c.y, in.ego_yaw_deg[f], d.target_lane, c.d, c.vd, d.sc,
+               out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN, flags, sp, tf);
+    double *e = sc.est + f;
+    e[0 * sc.n] = d.sc.start;
+    e[1 * sc.n] = d.sc.target;
+    e[2 * sc.n] = d.sc.time;
+    e[3 * sc.n] = tf.cx;
+    e[4 * sc.n] = tf.cy;
+    e[5 * sc.n] = tf.ca;
+    e[6 * sc.n] = tf.sa;
+    sc.e_np[f] = tf.np;
+    if (tf.fallback) {  // :848 the angle-based generator: its own (converged) kernel
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        e[(kEstHead + k) * sc.n] = tf.cpx[k];
+        e[(kEstHead + 6 + k) * sc.n] = tf.cpy[k];
+      }
+      sc.e_nk[f] = kEstFallback | tf.ncp;
+      sc.e_flags[f] = flags | PP_F_FALLBACK;
+      sc.slow_qa[atomicAdd(sc.slow_na, 1)] = (int32_t)f;
+      continue;
     }
+    spline_fit(sp);
+    const int r0 = tf.min_count > 0 ? tf.min_count - 1 : 0;
+    const int cnt = tf.nk - r0;
+    for (int k = 0; k < cnt; k++) {
+      e[(kEstHead + 0 * PPD_TAILK + k) * sc.n] = sp.x[r0 + k];
+      e[(kEstHead + 1 * PPD_TAILK + k) * sc.n] = sp.y[r0 + k];
+      e[(kEstHead + 2 * PPD_TAILK + k) * sc.n] = sp.a[r0 + k];
+      e[(kEstHead + 3 * PPD_TAILK + k) * sc.n] = sp.b[r0 + k];
+      e[(kEstHead + 4 * PPD_TAILK + k) * sc.n] = sp.c[r0 + k];
+    }
+    sc.e_nk[f] = cnt | (r0 > 0 ? kEstPartial : 0);
+    sc.e_flags[f] = flags;
+  }
+}
+
+// The emission loop (one thread per frame): no map, no spline fit, no library
+// transcendental — small code, few registers, many resident warps.  The
+// reachable knots are staged in shared memory (one column per thread).  A frame
+// that leaves the ranges the fast forms cover re-plans through k_slow.
+#ifndef PP_EMIT_MINB
+#define PP_EMIT_MINB 1
+#endif
+__global__ void __launch_bounds__(kBlock, PP_EMIT_MINB)
+k_emit(const __grid_constant__ pp_config cfg, const __grid_constant__ pp_plans out,
+       const __grid_constant__ Scratch sc, int64_t n) {
+  extern __shared__ double s_knots[];  // [5 * PPD_TAILK][blockDim.x]
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += stride) {
+    const int code = sc.e_nk[f];
+    if (code & kEstFallback) continue;  // queued for k_fallback
+    const int cnt = code & (kEstPartial - 1);
+    const double *e = sc.est + f;
+    SpeedCtl ctl;
+    ctl.shift = 0;
+    ctl.start = e[0 * sc.n];
+    ctl.target = e[1 * sc.n];
+    ctl.time = e[2 * sc.n];
+    const double cx = e[3 * sc.n], cy = e[4 * sc.n], ca = e[5 * sc.n], sa = e[6 * sc.n];
+    double *col = s_knots + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < 5; r++)
+      for (int k = 0; k < cnt; k++)
+        col[(r * PPD_TAILK + k) * blockDim.x] = e[(kEstHead + r * PPD_TAILK + k) * sc.n];
+    KnotsTail kn;
+    kn.base = col;
+    kn.stride = blockDim.x;
+    kn.count = cnt;
+    kn.part = (code & kEstPartial) != 0;
+    uint32_t flags = sc.e_flags[f];
+    int bail;
+    const int np = traj_emit<true>(kn, cfg, ctl, cx, cy, ca, sa, sc.e_np[f],
+                                   out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN,
+                                   flags, bail);
+    if (bail) {
+      sc.slow_qb[atomicAdd(sc.slow_nb, 1)] = (int32_t)f;
+      if (sc.dbg) atomicAdd(sc.dbg + bail, 1);
+      continue;
+    }
+    store_path_tail(out, f, np, flags);
+  }
+}
+
+// The angle-based generator (:848-901) for the frames k_decide queued.  Every
+// lane runs the same loop, so the queue is consumed densely (32 frames a warp).
+__global__ void __launch_bounds__(kBlock)
+k_fallback(const __grid_constant__ pp_plans out, const __grid_constant__ Scratch sc,
+           const int32_t *__restrict__ queue, const int32_t *__restrict__ queue_n) {
+  const int count = *queue_n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < count; q += stride) {
+    const int64_t f = queue[q];
+    const double *e = sc.est + f;
+    SpeedCtl ctl;
+    ctl.shift = 0;
+    ctl.start = e[0 * sc.n];
+    ctl.target = e[1 * sc.n];
+    ctl.time = e[2 * sc.n];
+    TrajFrame tf;
+    tf.cx = e[3 * sc.n];
+    tf.cy = e[4 * sc.n];
+    tf.ca = e[5 * sc.n];
+    tf.sa = e[6 * sc.n];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      tf.cpx[k] = e[(kEstHead + k) * sc.n];
+      tf.cpy[k] = e[(kEstHead + 6 + k) * sc.n];
+    }
+    tf.np = sc.e_np[f];
+    tf.ncp = sc.e_nk[f] & 0xff;
+    const int np = traj_fallback(tf, ctl, out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN);
+    store_path_tail(out, f, np, sc.e_flags[f]);
+  }
+}
+
+// The complete path for the frames k_emit gave up on (a few hundred per
+// million: headings or frame rotations outside the ranges its fast forms
+// cover, arguments left of the staged knots).  Every such frame takes its own
+// route through the code, so each gets a warp of its own (lane 0): nothing is
+// serialised behind another frame's branches.
+constexpr int kSlowSpread = 32;
+__global__ void __launch_bounds__(kBlock)
+k_slow(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
+       const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
+       const __grid_constant__ Scratch sc, const int32_t *__restrict__ queue,
+       const int32_t *__restrict__ queue_n) {
+  const int count = *queue_n;
+  const int per_block = kBlock / kSlowSpread;
+  if ((int64_t)blockIdx.x * per_block >= count) return;
+  extern __shared__ double s_map[];
+  const MapView m = stage_map(s_map, map_table, n_wp);
+  if (threadIdx.x % kSlowSpread) return;
+  const int64_t stride = (int64_t)gridDim.x * per_block;
+  for (int64_t q = (int64_t)blockIdx.x * per_block + threadIdx.x / kSlowSpread; q < count;
+       q += stride) {
+    const int64_t f = queue[q];
+    FrameCtx c;
+    load_ctx(sc, f, c);
+    uint32_t flags = c.flags;
+    const int tl_in = in.target_lane_in[f];
+    Behav b;
+    reduce_cars(cfg, in, sc, f, c, tl_in, b, flags);
     stage_finish(m, cfg, in, out, f, c, b, tl_in, flags);
   }
 }
@@ -470,9 +681,51 @@ stats_kernel(const __grid_constant__ pp_plans p, int64_t n, unsigned long long *
 int g_variant = 0;
 int g_sm_count = 0;
 
+// ---- side stream for the rare-frame kernel (one per host thread and device)
+struct Side {
+  int dev = -1;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};
+  int ensure() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) return PP_E_CUDA;
+    if (st && d == dev) return PP_OK;
+    release();
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_done[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_done[1], cudaEventDisableTiming) != cudaSuccess) {
+      cudaError_t e = cudaGetLastError();
+      ppi::set_cuda_error("side stream", (int)e, cudaGetErrorString(e));
+      release();
+      return PP_E_CUDA;
+    }
+    dev = d;
+    return PP_OK;
+  }
+  void release() {
+    if (ev_a) cudaEventDestroy(ev_a);
+    if (ev_b) cudaEventDestroy(ev_b);
+    if (ev_join) cudaEventDestroy(ev_join);
+    for (int i = 0; i < 2; i++) {
+      if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+      ev_done[i] = nullptr;
+    }
+    if (st) cudaStreamDestroy(st);
+    ev_a = ev_b = ev_join = nullptr;
+    st = nullptr;
+    dev = -1;
+  }
+  // not destroyed at thread exit: the CUDA context may already be gone by then
+};
+thread_local Side t_side;
+
 // ---- optional per-phase timing (bench.py / profiles): CUDA events recorded on
 // the caller's stream around every kernel of the pipeline.
-constexpr int kPhases = 3;  // prep, cars, plan
+constexpr int kPhases = 5;  // prep, cars, decide, emit, slow
 constexpr int kMaxTimedChunks = 4096;
 bool g_phase_timing = false;
 struct PhaseEvents {
@@ -623,7 +876,10 @@ extern "C" int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_f
   if ((rc = ensure_smem(plan_fused, smem)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_prep, smem)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_cars, smem)) != PP_OK) return rc;
-  if ((rc = ensure_smem(k_plan, smem)) != PP_OK) return rc;
+  if ((rc = ensure_smem(k_decide, smem)) != PP_OK) return rc;
+  if ((rc = ensure_smem(k_slow, smem)) != PP_OK) return rc;
+  const size_t smem_emit = (size_t)5 * PPD_TAILK * kBlock * sizeof(double);
+  if ((rc = ensure_smem(k_emit, smem_emit)) != PP_OK) return rc;
 
   const bool fused = g_variant == 1 || (g_variant == 0 && n_frames < kFusedBelow);
   if (fused) {
@@ -650,20 +906,43 @@ extern "C" int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_f
       pool_tuned[dev] = true;
     }
   }
+  Side &side = t_side;
+  if ((rc = side.ensure()) != PP_OK) return rc;
+  // Scratch is double buffered: the side stream may still be reading chunk i's while the
+  // main stream fills chunk i+1's.
+  const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
+  const int n_buf = n_chunks > 1 ? 2 : 1;
+  const size_t scratch = (scratch_bytes(chunk, mc) + 255) & ~(size_t)255;
+  const size_t queues = (size_t)n_frames * 2 * sizeof(int32_t);
+  const size_t counters = (size_t)n_chunks * 2 * sizeof(int32_t);
   char *buf = nullptr;
-  cudaError_t e = cudaMallocAsync((void **)&buf, scratch_bytes(chunk, mc), st);
+  cudaError_t e = cudaMallocAsync((void **)&buf, n_buf * scratch + queues + counters + 256, st);
   if (e != cudaSuccess) {
     ppi::set_cuda_error("cudaMallocAsync(scratch)", (int)e, cudaGetErrorString(e));
     cudaGetLastError();
     return PP_E_CUDA;
   }
-  const Scratch sc = carve_scratch(buf, chunk, mc);
+  Scratch scs[2] = {carve_scratch(buf, chunk, mc), carve_scratch(buf + (n_buf - 1) * scratch, chunk, mc)};
+  int32_t *q_base = (int32_t *)(buf + n_buf * scratch);
+  int32_t *n_base = (int32_t *)(buf + n_buf * scratch + queues);
+  cudaMemsetAsync(n_base, 0, counters + 64, st);
+  static const bool dbg = getenv("PP_DEBUG_SLOW") != nullptr;  // diagnostic: queue lengths
   rc = PP_OK;
-  for (int64_t lo = 0; lo < n_frames && rc == PP_OK; lo += chunk) {
+  const int side_grid = sm_count() * 4;
+  int64_t ci = 0;
+  PhaseEvents *pe = nullptr;
+  for (int64_t lo = 0; lo < n_frames && rc == PP_OK; lo += chunk, ci++) {
     const int64_t cnt = (n_frames - lo) < chunk ? (n_frames - lo) : chunk;
     const pp_frames fin = offset_frames(*in, lo);
     const pp_plans fout = offset_plans(*out, lo, mc);
-    PhaseEvents *pe = phase_begin();
+    Scratch &sc = scs[ci & 1];
+    sc.slow_qa = q_base + 2 * lo;  // queue entries are chunk-relative frame numbers
+    sc.slow_qb = q_base + 2 * lo + cnt;
+    sc.slow_na = n_base + 2 * ci;
+    sc.slow_nb = n_base + 2 * ci + 1;
+    sc.dbg = dbg ? n_base + 2 * n_chunks : nullptr;
+    if (ci >= 2) cudaStreamWaitEvent(st, side.ev_done[ci & 1], 0);  // side work of chunk ci-2
+    pe = phase_begin();
     phase_mark(pe, 0, st);
     k_prep<<<grid_for(cnt, 12), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, fin, sc, cnt);
     phase_mark(pe, 1, st);
@@ -671,13 +950,45 @@ extern "C" int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_f
       k_cars<<<grid_for(cnt * mc, 12), kBlock, smem, st>>>(map->dev_table, map->n, fin, fout, sc,
                                                            cnt);
     phase_mark(pe, 2, st);
-    k_plan<<<grid_for(cnt, 12), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, fin, fout, sc,
-                                                    cnt);
+    k_decide<<<grid_for(cnt, 12), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, fin, fout, sc,
+                                                      cnt);
     phase_mark(pe, 3, st);
-    ppi::count_launch(mc > 0 ? 3 : 2);
+    // side stream: the frames k_decide queued, concurrently with k_emit and the next chunk
+    cudaEventRecord(side.ev_a, st);
+    cudaStreamWaitEvent(side.st, side.ev_a, 0);
+    k_fallback<<<side_grid, kBlock, 0, side.st>>>(fout, sc, sc.slow_qa, sc.slow_na);
+    k_emit<<<grid_for(cnt, 12), kBlock, smem_emit, st>>>(*cfg, fout, sc, cnt);
+    phase_mark(pe, 4, st);
+    cudaEventRecord(side.ev_b, st);
+    cudaStreamWaitEvent(side.st, side.ev_b, 0);
+    k_slow<<<side_grid, kBlock, smem, side.st>>>(map->dev_table, map->n, *cfg, fin, fout, sc,
+                                                 sc.slow_qb, sc.slow_nb);
+    cudaEventRecord(side.ev_done[ci & 1], side.st);
+    ppi::count_launch(mc > 0 ? 6 : 5);
     rc = check_launch("plan pipeline");
+    if (lo + chunk < n_frames) phase_mark(pe, 5, st);
+  }
+  // join: the caller's stream continues only after the queued frames are planned
+  cudaEventRecord(side.ev_join, side.st);
+  cudaStreamWaitEvent(st, side.ev_join, 0);
+  phase_mark(pe, 5, st);
+  if (dbg) {
+    std::vector<int32_t> h((size_t)n_chunks * 2 + 8);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), n_base, counters + 32, cudaMemcpyDeviceToHost);
+    long a = 0, b = 0;
+    for (int64_t i = 0; i < n_chunks; i++) {
+      a += h[2 * i];
+      b += h[2 * i + 1];
+    }
+    const int32_t *r = h.data() + 2 * n_chunks;
+    std::fprintf(stderr,
+                 "pp_plan_batch: %lld frames, queued by k_decide %ld, by k_emit %ld (knots %d, "
+                 "atan2 %d, fmod %d, sincos %d)\n",
+                 (long long)n_frames, a, b, r[1], r[2], r[3], r[4]);
   }
   cudaFreeAsync(buf, st);
+  if (rc == PP_OK) rc = check_launch("plan pipeline join");
   return rc;
 }
 

@@ -226,9 +226,10 @@ __global__ void k_selftest_math(int64_t n, unsigned long long seed, unsigned lon
   const double f = fmod_near(x, m), fe = fmod(x, m);
   if (__double_as_longlong(f) != __double_as_longlong(fe)) atomicAdd(&counts[2], 1ull);
   st = mix64(st);
-  const double dx = 0.001 + 0.5 * ((double)(st >> 11) * (1.0 / 9007199254740992.0));
+  double dx = 0.001 + 0.5 * ((double)(st >> 11) * (1.0 / 9007199254740992.0));
+  if ((i & 7) == 3) dx = -dx;  // all four quadrants
   st = mix64(st);
-  const double dy = dx * 3.0 * (2.0 * ((double)(st >> 11) * (1.0 / 9007199254740992.0)) - 1.0);
+  const double dy = fabs(dx) * 3.0 * (2.0 * ((double)(st >> 11) * (1.0 / 9007199254740992.0)) - 1.0);
   const double t1 = atan2_step(dy, dx), t2 = atan2(dy, dx);
   long long d = __double_as_longlong(t1) - __double_as_longlong(t2);
   if (d < 0) d = -d;

@@ -202,8 +202,11 @@ int pp_set_kernel_variant(int variant);
 /* Measurement aid (bench.py): when on, pp_plan_batch records CUDA events on the
  * caller's stream around each kernel of the pipeline.  pp_get_phase_ms waits for
  * the last of them and returns the summed device time in ms of ms_out[0] = ego
- * preparation, [1] = per-car matching, [2] = decision + trajectory over all
- * chunks launched since the previous call (chunks_out, may be NULL). */
+ * preparation, [1] = per-car matching, [2] = decision + spline fit, [3] = point
+ * emission, [4] = complete path for the queued rare frames (PP_NUM_PHASES
+ * values) over all chunks launched since the previous call (chunks_out, may be
+ * NULL). */
+#define PP_NUM_PHASES 5
 int pp_set_phase_timing(int on);
 int pp_get_phase_ms(double *ms_out, int64_t *chunks_out);
 /* Number of kernel launches issued by this library since load (bench.py's

@@ -24,5 +24,5 @@ for rep in range(3):
         for _ in range(5): pp.plan_batch(m, df, dp)
         ms, ch = pp.get_phase_ms()
         pp.set_phase_timing(False)
-        print("phases ms/call: prep %.3f cars %.3f plan %.3f (chunks %d)" % (ms[0]/5, ms[1]/5, ms[2]/5, ch))
+        print("phases ms/call: prep %.3f cars %.3f decide %.3f emit %.3f slow %.3f (chunks %d)" % (*[v/5 for v in ms], ch))
     print(f"variant {v} n {n}: host issue {1e3*(t1-t0)/5:.3f} ms/call, device {e0.elapsed_time(e1)/5:.3f} ms/call, wall {1e3*(t2-t0)/5:.3f} ms/call")
