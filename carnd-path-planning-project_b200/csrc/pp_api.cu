@@ -36,7 +36,17 @@ int upload_map(pp_map *m) {
     cudaGetLastError();
     return PP_E_CUDA;
   }
-  const size_t bytes = m->table.size() * sizeof(double);
+  // device copy = the table padded with PPD_PAD wrapped rows at both ends (pp_device.cuh)
+  const int pad = 24;
+  static_assert(pad == PPD_PAD_ROWS, "padding must match the device code");
+  std::vector<double> padded((size_t)(m->n + 2 * pad) * PP_MAP_STRIDE);
+  for (int r = 0; r < m->n + 2 * pad; r++) {
+    int src = (r - pad) % m->n;
+    if (src < 0) src += m->n;
+    std::memcpy(&padded[(size_t)r * PP_MAP_STRIDE], &m->table[(size_t)src * PP_MAP_STRIDE],
+                PP_MAP_STRIDE * sizeof(double));
+  }
+  const size_t bytes = padded.size() * sizeof(double);
   e = cudaMalloc(&m->dev_table, bytes);
   if (e != cudaSuccess) {
     m->dev_table = nullptr;
@@ -44,7 +54,7 @@ int upload_map(pp_map *m) {
     cudaGetLastError();
     return PP_E_CUDA;
   }
-  e = cudaMemcpy(m->dev_table, m->table.data(), bytes, cudaMemcpyHostToDevice);
+  e = cudaMemcpy(m->dev_table, padded.data(), bytes, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     cudaFree(m->dev_table);
     m->dev_table = nullptr;

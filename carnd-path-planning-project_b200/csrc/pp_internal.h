@@ -5,10 +5,13 @@
 
 #include "../../include/pp.h"
 
+// rows of wrap-around padding on either side of the device copy of the table
+#define PPD_PAD_ROWS 24
+
 struct pp_map {
   int n = 0;                  // waypoints
   std::vector<double> table;  // n * PP_MAP_STRIDE, host copy (row layout of pp.h)
-  double *dev_table = nullptr;  // device copy (nullptr if no CUDA device was usable)
+  double *dev_table = nullptr;  // device copy, padded (nullptr if no CUDA device was usable)
   int device = -1;              // CUDA device the table lives on
 };
 

@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kBlock)
 plan_fused(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
            const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
            int64_t n_frames) {
-  extern __shared__ double s_map[];
+  extern __shared__ __align__(16) double s_map[];
   const MapView m = stage_map(s_map, map_table, n_wp);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_frames; f += stride)
@@ -325,7 +325,7 @@ struct Scratch {
   int32_t *wp, *lane, *nprev;
   uint32_t *flags;
   double *car_s, *car_d, *car_vs, *car_vd;  // [n][max_cars]
-  int32_t *car_lane, *car_wp;
+  int32_t *car_lane;
   // between k_decide and k_emit: SpeedController, local frame, the reachable knots
   double *est;         // [kEstRows][n]
   int32_t *e_np;       // points already written (kept previous points)
@@ -344,7 +344,7 @@ constexpr int kEstFallback = 1 << 9;  // e_nk = kEstFallback | ncp: state for k_
 
 size_t scratch_bytes(int64_t n, int mc) {
   const size_t per_frame = 11 * 8 + 4 * 4 + (size_t)kEstRows * 8 + 3 * 4;
-  const size_t per_car = 4 * 8 + 2 * 4;
+  const size_t per_car = 4 * 8 + 4;
   return (size_t)n * (per_frame + (size_t)mc * per_car) + 64 * 256;
 }
 
@@ -375,7 +375,6 @@ Scratch carve_scratch(char *base, int64_t n, int mc) {
   s.car_vs = (double *)take(NC * 8);
   s.car_vd = (double *)take(NC * 8);
   s.car_lane = (int32_t *)take(NC * 4);
-  s.car_wp = (int32_t *)take(NC * 4);
   s.est = (double *)take((size_t)kEstRows * N * 8);
   s.e_np = (int32_t *)take(N * 4);
   s.e_nk = (int32_t *)take(N * 4);
@@ -389,7 +388,7 @@ Scratch carve_scratch(char *base, int64_t n, int mc) {
 __global__ void __launch_bounds__(kBlock, PP_PREP_MINB)
 k_prep(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
        const __grid_constant__ pp_frames in, const __grid_constant__ Scratch sc, int64_t n) {
-  extern __shared__ double s_map[];
+  extern __shared__ __align__(16) double s_map[];
   const MapView m = stage_map(s_map, map_table, n_wp);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += stride) {
@@ -415,7 +414,7 @@ k_prep(const double *__restrict__ map_table, int n_wp, const __grid_constant__ p
 __global__ void __launch_bounds__(kBlock, PP_CARS_MINB)
 k_cars(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_frames in,
        const __grid_constant__ pp_plans out, const __grid_constant__ Scratch sc, int64_t n) {
-  extern __shared__ double s_map[];
+  extern __shared__ __align__(16) double s_map[];
   const MapView m = stage_map(s_map, map_table, n_wp);
   const int mc = in.max_cars;
   const int64_t total = n * mc;
@@ -430,12 +429,12 @@ k_cars(const double *__restrict__ map_table, int n_wp, const __grid_constant__ p
     rs.ratio[1] = sc.ratio[sc.n + f];
     rs.ratio[2] = sc.ratio[2 * sc.n + f];
     const CarRes r = stage_car(m, rs, in.car_x[t], in.car_y[t], in.car_vx[t], in.car_vy[t]);
-    sc.car_s[t] = r.s;
-    sc.car_d[t] = r.d;
-    sc.car_vs[t] = r.vs;
-    sc.car_vd[t] = r.vd;
-    sc.car_lane[t] = r.lane;
-    sc.car_wp[t] = r.wp;
+    const int64_t slot = (int64_t)j * sc.n + f;  // car-major: k_decide reads it coalesced
+    sc.car_s[slot] = r.s;
+    sc.car_d[slot] = r.d;
+    sc.car_vs[slot] = r.vs;
+    sc.car_vd[slot] = r.vd;
+    sc.car_lane[slot] = r.lane;
     store_car(out, t, r);
   }
 }
@@ -466,15 +465,25 @@ PPD_INLINE void reduce_cars(const pp_config &cfg, const pp_frames &in, const Scr
   if (nc > mc) nc = mc;
   behav_init(b, cfg);
   const int64_t cb = f * mc;
+  // car j + 1 is loaded while car j is reduced (the loads are coalesced: car-major scratch)
+  CarRes nxt;
+  int nxt_id = 0;
+  auto fetch = [&](int j) {
+    const int64_t slot = (int64_t)j * sc.n + f;
+    nxt.lane = sc.car_lane[slot];
+    nxt.wp = 0;
+    nxt.s = sc.car_s[slot];
+    nxt.d = sc.car_d[slot];
+    nxt.vs = sc.car_vs[slot];
+    nxt.vd = sc.car_vd[slot];
+    nxt_id = in.car_id[cb + j];
+  };
+  if (nc > 0) fetch(0);
   for (int j = 0; j < nc; j++) {
-    CarRes r;
-    r.lane = sc.car_lane[cb + j];
-    r.wp = sc.car_wp[cb + j];
-    r.s = sc.car_s[cb + j];
-    r.d = sc.car_d[cb + j];
-    r.vs = sc.car_vs[cb + j];
-    r.vd = sc.car_vd[cb + j];
-    behav_add(b, cfg, c, tl_in, in.car_id[cb + j], j, r, flags);
+    const CarRes r = nxt;
+    const int id = nxt_id;
+    if (j + 1 < nc) fetch(j + 1);
+    behav_add(b, cfg, c, tl_in, id, j, r, flags);
   }
 }
 
@@ -485,7 +494,7 @@ __global__ void __launch_bounds__(kBlock, PP_PLAN_MINB)
 k_decide(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
          const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
          const __grid_constant__ Scratch sc, int64_t n) {
-  extern __shared__ double s_map[];
+  extern __shared__ __align__(16) double s_map[];
   const MapView m = stage_map(s_map, map_table, n_wp);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += stride) {
@@ -561,10 +570,16 @@ k_emit(const __grid_constant__ pp_config cfg, const __grid_constant__ pp_plans o
     ctl.time = e[2 * sc.n];
     const double cx = e[3 * sc.n], cy = e[4 * sc.n], ca = e[5 * sc.n], sa = e[6 * sc.n];
     double *col = s_knots + threadIdx.x;
+    // all 35 slots, unconditionally: fixed trip counts let the loads of a row go out
+    // together (slots past cnt hold stale values that are never read)
 #pragma unroll
-    for (int r = 0; r < 5; r++)
-      for (int k = 0; k < cnt; k++)
-        col[(r * PPD_TAILK + k) * blockDim.x] = e[(kEstHead + r * PPD_TAILK + k) * sc.n];
+    for (int r = 0; r < 5; r++) {
+      double tmp[PPD_TAILK];
+#pragma unroll
+      for (int k = 0; k < PPD_TAILK; k++) tmp[k] = e[(kEstHead + r * PPD_TAILK + k) * sc.n];
+#pragma unroll
+      for (int k = 0; k < PPD_TAILK; k++) col[(r * PPD_TAILK + k) * blockDim.x] = tmp[k];
+    }
     KnotsTail kn;
     kn.base = col;
     kn.stride = blockDim.x;
@@ -630,7 +645,7 @@ k_slow(const double *__restrict__ map_table, int n_wp, const __grid_constant__ p
   const int count = *queue_n;
   const int per_block = kBlock / kSlowSpread;
   if ((int64_t)blockIdx.x * per_block >= count) return;
-  extern __shared__ double s_map[];
+  extern __shared__ __align__(16) double s_map[];
   const MapView m = stage_map(s_map, map_table, n_wp);
   if (threadIdx.x % kSlowSpread) return;
   const int64_t stride = (int64_t)gridDim.x * per_block;

@@ -29,7 +29,7 @@ __global__ void k_pt_seg(const double *px, const double *py, const double *ax, c
 
 __global__ void k_init_reference(const double *table, int n_wp, const double *x, const double *y,
                                  int32_t *wp, double *ratio, int64_t n) {
-  extern __shared__ double s_map[];
+  extern __shared__ __align__(16) double s_map[];
   const MapView m = stage_map(s_map, table, n_wp);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -45,7 +45,7 @@ __global__ void k_lane_matching(const double *table, int n_wp, const double *rx,
                                 const double *x, const double *y, const double *vx,
                                 const double *vy, int32_t *ok, int32_t *lane, int32_t *next_wp,
                                 double *s, double *d, double *vs, double *vd, int64_t n) {
-  extern __shared__ double s_map[];
+  extern __shared__ __align__(16) double s_map[];
   const MapView m = stage_map(s_map, table, n_wp);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -66,7 +66,7 @@ __global__ void k_lane_matching(const double *table, int n_wp, const double *rx,
 __global__ void k_lane_pos(const double *table, int n_wp, const double *rx, const double *ry,
                            const double *s, const int32_t *lane, double *ox, double *oy,
                            int32_t *owp, double *odist, int64_t n) {
-  extern __shared__ double s_map[];
+  extern __shared__ __align__(16) double s_map[];
   const MapView m = stage_map(s_map, table, n_wp);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -163,7 +163,7 @@ __global__ void k_trajectory(const double *table, int n_wp, const __grid_constan
                              const double *sc_start, const double *sc_target,
                              const double *sc_time, double *out_x, double *out_y, int32_t *out_n,
                              uint32_t *out_flags, int64_t n) {
-  extern __shared__ double s_map[];
+  extern __shared__ __align__(16) double s_map[];
   const MapView m = stage_map(s_map, table, n_wp);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

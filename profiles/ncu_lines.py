@@ -98,3 +98,15 @@ for nm, v in sorted(per_func.items(), key=lambda t: -t[1][0]):
 print(f"\n-- top {top} source lines by samples")
 for key, v in sorted(per_line.items(), key=lambda t: -t[1][0])[:top]:
     print(f"{str(key):34s} {100*v[0]/tot[0]:6.2f}%  inst {100*v[1]/tot[1]:6.2f}%  lanes {v[2]/max(v[1],1):5.1f}  no_inst {100*v[3]/max(v[0],1):5.1f}%")
+
+# lane-occupancy histogram of the instruction stream
+buckets = collections.OrderedDict((("1-4", 0), ("5-12", 0), ("13-24", 0), ("25-30", 0), ("31-32", 0)))
+for key, v in per_line.items():
+    if not v[1]:
+        continue
+    l = v[2] / v[1]
+    b = "1-4" if l <= 4.5 else "5-12" if l <= 12.5 else "13-24" if l <= 24.5 else "25-30" if l <= 30.5 else "31-32"
+    buckets[b] += v[1]
+print("\n-- warp instructions by average active lanes of their source line")
+for b, n in buckets.items():
+    print(f"  lanes {b:6s} {100*n/tot[1]:6.1f} %")
