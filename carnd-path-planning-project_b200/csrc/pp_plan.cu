@@ -40,14 +40,16 @@ using namespace ppd;
 constexpr int kBlock = 128;
 // minimum resident blocks per SM the compiler must allow for (register budget);
 // tuned with ncu, see profiles/
+// (profiles/sweep_minb.sh, gpurun_out/sweep2.log: prep 5 / cars 6 / decide 4 each gain 4-7 %;
+// forcing the emission kernel below its natural 116 registers loses)
 #ifndef PP_PREP_MINB
-#define PP_PREP_MINB 1
+#define PP_PREP_MINB 5
 #endif
 #ifndef PP_CARS_MINB
-#define PP_CARS_MINB 1
+#define PP_CARS_MINB 6
 #endif
 #ifndef PP_PLAN_MINB
-#define PP_PLAN_MINB 1
+#define PP_PLAN_MINB 4
 #endif
 
 // ---------------------------------------------------------------------------
@@ -411,31 +413,94 @@ k_prep(const double *__restrict__ map_table, int n_wp, const __grid_constant__ p
   }
 }
 
+// One thread per car.  The number of segments a car's walk takes grows with its
+// distance from the ego along the road, and a warp advances at the pace of its
+// longest walk (ncu, profiles/r1c: 75 % of this kernel's instructions were in
+// the walk loop at 13 of 32 lanes).  So each warp takes a tile of 32 x kTileK
+// consecutive car slots, bins them by a cheap proxy of the walk length
+// (distance to the ego in units of the local segment length), counting-sorts
+// the tile in shared memory and then walks 32 cars of similar length at a time.
+// The proxy only orders the work; results do not depend on it.
+#ifndef PP_TILE_K
+#define PP_TILE_K 8
+#endif
+constexpr int kTileK = PP_TILE_K;      // cars per lane per tile
+constexpr int kTile = 32 * kTileK;     // car slots per tile
+constexpr int kBins = 24;              // proxy bins; bin kBins = slot holds no car
 __global__ void __launch_bounds__(kBlock, PP_CARS_MINB)
 k_cars(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_frames in,
        const __grid_constant__ pp_plans out, const __grid_constant__ Scratch sc, int64_t n) {
   extern __shared__ __align__(16) double s_map[];
+  __shared__ int s_hist[kBlock / 32][32];
+  __shared__ unsigned short s_order[kBlock / 32][kTile];
   const MapView m = stage_map(s_map, map_table, n_wp);
   const int mc = in.max_cars;
   const int64_t total = n * mc;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-    const int64_t f = t / mc;
-    const int j = (int)(t - f * mc);
-    if (j >= in.n_cars[f]) continue;
-    RefState rs;
-    rs.wp = sc.wp[f];
-    rs.ratio[0] = sc.ratio[f];
-    rs.ratio[1] = sc.ratio[sc.n + f];
-    rs.ratio[2] = sc.ratio[2 * sc.n + f];
-    const CarRes r = stage_car(m, rs, in.car_x[t], in.car_y[t], in.car_vx[t], in.car_vy[t]);
-    const int64_t slot = (int64_t)j * sc.n + f;  // car-major: k_decide reads it coalesced
-    sc.car_s[slot] = r.s;
-    sc.car_d[slot] = r.d;
-    sc.car_vs[slot] = r.vs;
-    sc.car_vd[slot] = r.vd;
-    sc.car_lane[slot] = r.lane;
-    store_car(out, t, r);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int *hist = s_hist[wib];
+  unsigned short *order = s_order[wib];
+  const int64_t n_tiles = (total + kTile - 1) / kTile;
+  const int64_t warps = (int64_t)gridDim.x * (kBlock / 32);
+  for (int64_t tile = (int64_t)blockIdx.x * (kBlock / 32) + wib; tile < n_tiles; tile += warps) {
+    const int64_t base = tile * kTile;
+    // ---- bin the tile's cars
+    hist[lane] = 0;
+    __syncwarp();
+    int key[kTileK];  // bin | rank within the bin << 8
+#pragma unroll
+    for (int k = 0; k < kTileK; k++) {
+      const int64_t t = base + k * 32 + lane;
+      int bin = kBins;
+      if (t < total) {
+        const int64_t f = t / mc;
+        const int j = (int)(t - f * mc);
+        if (j < in.n_cars[f]) {
+          const float dx = (float)(in.car_x[t] - sc.x[f]), dy = (float)(in.car_y[t] - sc.y[f]);
+          const int wp = sc.wp[f];
+          const float len = (float)row(m, wp)[11];  // centre lane's segment length
+          const float q = sqrtf(dx * dx + dy * dy) / len;
+          bin = q < (float)(kBins - 1) ? (int)q : kBins - 1;  // NaN -> last bin
+        }
+      }
+      key[k] = bin | (atomicAdd(&hist[bin], 1) << 8);
+    }
+    __syncwarp();
+    // exclusive prefix over the bins (lane b owns bin b)
+    const int cnt = hist[lane];
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    __syncwarp();
+    hist[lane] = incl - cnt;
+    __syncwarp();
+    const int n_valid = hist[kBins];
+#pragma unroll
+    for (int k = 0; k < kTileK; k++)
+      order[hist[key[k] & 0xff] + (key[k] >> 8)] = (unsigned short)(k * 32 + lane);
+    __syncwarp();
+    // ---- walk them, 32 of similar length at a time
+    for (int g = lane; g < n_valid; g += 32) {
+      const int64_t t = base + order[g];
+      const int64_t f = t / mc;
+      const int j = (int)(t - f * mc);
+      RefState rs;
+      rs.wp = sc.wp[f];
+      rs.ratio[0] = sc.ratio[f];
+      rs.ratio[1] = sc.ratio[sc.n + f];
+      rs.ratio[2] = sc.ratio[2 * sc.n + f];
+      const CarRes r = stage_car(m, rs, in.car_x[t], in.car_y[t], in.car_vx[t], in.car_vy[t]);
+      const int64_t slot = (int64_t)j * sc.n + f;  // car-major: k_decide reads it coalesced
+      sc.car_s[slot] = r.s;
+      sc.car_d[slot] = r.d;
+      sc.car_vs[slot] = r.vs;
+      sc.car_vd[slot] = r.vd;
+      sc.car_lane[slot] = r.lane;
+      store_car(out, t, r);
+    }
+    __syncwarp();
   }
 }
 
@@ -962,7 +1027,7 @@ extern "C" int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_f
     k_prep<<<grid_for(cnt, 12), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, fin, sc, cnt);
     phase_mark(pe, 1, st);
     if (mc > 0)
-      k_cars<<<grid_for(cnt * mc, 12), kBlock, smem, st>>>(map->dev_table, map->n, fin, fout, sc,
+      k_cars<<<grid_for((cnt * mc + kTileK - 1) / kTileK, 12), kBlock, smem, st>>>(map->dev_table, map->n, fin, fout, sc,
                                                            cnt);
     phase_mark(pe, 2, st);
     k_decide<<<grid_for(cnt, 12), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, fin, fout, sc,
