@@ -4,6 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
+Default run: N=1, 50 timed steps after 3 warm-ups (a few seconds).
+
 One "step" = one pass of the hot path (pp_plan_batch, then the aggregate
 statistics kernel; for N>1 followed by the NCCL all-reduce of the statistics
 vector — the only collective on the path) over one batch of synthetic frames
@@ -111,61 +113,73 @@ def run_reference(args):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled every ~5 ms through NVML on a thread while the
+    timed region runs (nvidia-smi's own loop is too coarse for a sub-second region)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+        self.samples, self.maxes, self.reasons = [], [], set()
+        self.stop_flag = False
+        self.ok = False
         try:
-            self.p = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-i", str(index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = None
+            try:  # the CUDA ordinal need not be the NVML index (CUDA_VISIBLE_DEVICES)
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self.h = None
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
         except Exception:
-            self.p = None
+            self.ok = False
+        self.t = threading.Thread(target=self._run, daemon=True)
+        if self.ok:
+            self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) \
+                    if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.ok:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.f.read().splitlines():
-            c = [x.strip() for x in ln.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if c[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        os.unlink(self.f.name)
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        sm = sorted(self.samples)
         if sm:
-            sm.sort()
-            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz,
+                   "reasons": sorted(self.reasons), "samples": len(sm)}
         return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--variant", type=int, default=0)
     args = ap.parse_args()
@@ -217,6 +231,7 @@ def main():
     k_stop = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = pp.launch_count()
+    pp.set_phase_timing(True)   # CUDA events around every kernel of the pipeline (same stream)
     fence()
     ev0.record(stream)
     for i in range(args.steps):
@@ -230,6 +245,9 @@ def main():
     fence()
     launches = pp.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
+    phase_ms, phase_chunks = pp.get_phase_ms()
+    pp.set_phase_timing(False)
+    phase_ms = [v / args.steps for v in phase_ms]
     total_ms = ev0.elapsed_time(ev1)
     kern_ms = sum(a.elapsed_time(b) for a, b in zip(k_start, k_stop)) / args.steps
     t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device="cuda")
@@ -267,13 +285,23 @@ def main():
         peak, peak_src = peaks()
         alg_bytes = (BYTES_IN + BYTES_OUT) * n
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        traffic = None
+        # dram__bytes_read+write of the pipeline's kernels from the committed ncu capture
+        # (profiles/traffic.json: bytes per 262,144-frame launch, summed over the kernels)
+        traffic, traffic_by_kernel = None, {}
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             try:
-                traffic = json.load(open(prof)).get("plan_kernel_dram_bytes_per_launch")
+                tj = json.load(open(prof))
+                traffic_by_kernel = tj.get("dram_bytes_per_launch", {})
+                per_frame = sum(traffic_by_kernel.values()) / float(tj["frames_per_launch"])
+                traffic = per_frame * n
             except Exception:
-                traffic = None
+                traffic, traffic_by_kernel = None, {}
+        names = ["k_prep", "k_cars", "k_decide", "k_emit", "side-stream tail (k_fallback/k_slow join)"]
+        pipe_ms = sum(phase_ms)
+        kernels = [{"name": nm, "ms_per_step": ms, "share": ms / pipe_ms if pipe_ms else None,
+                    "launches_per_step": phase_chunks // args.steps if nm[0] == "k" else None}
+                   for nm, ms in zip(names, phase_ms)]
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -290,9 +318,14 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "plan_thread_per_frame", "kernel_ms": kern_ms,
+                         "kernel": "pp_plan_batch pipeline (k_prep + k_cars + k_decide + k_emit, "
+                                   "4 chunks of 262,144 frames per step); dominant: "
+                                   + max(kernels[:4], key=lambda k: k["ms_per_step"])["name"],
+                         "kernel_ms": kern_ms, "kernels": kernels,
                          "algorithmic_bytes_per_frame": BYTES_IN + BYTES_OUT,
-                         "note": "this kernel is FP64-issue/latency bound, not HBM bound: see DESIGN.md §2"},
+                         "algorithmic_bytes_per_step": alg_bytes,
+                         "note": "FP64-issue / divergence bound, not HBM bound (DESIGN.md §2): "
+                                 "1,520 B against ~35 k FP64-heavy instructions per frame"},
             "clocks": clocks,
             "stats": {"frames": int(stats[0]), "points": int(stats[1]),
                       "lane_changes": int(stats[8])},

@@ -728,30 +728,72 @@ k_slow(const double *__restrict__ map_table, int n_wp, const __grid_constant__ p
 }
 
 // ---- aggregate statistics: exact int64 sums -----------------
+// HBM bound (re-reads the plans: 828 B/frame).  The trajectories are read as one
+// flat array (coalesced; the owning frame's n_points masks the padding), the
+// per-frame scalars in a second pass with warp ballots instead of one atomic per
+// frame and flag.
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
 __global__ void __launch_bounds__(256)
 stats_kernel(const __grid_constant__ pp_plans p, int64_t n, unsigned long long *stats) {
   __shared__ unsigned long long s_acc[PP_STATS_LEN];
   for (int i = threadIdx.x; i < PP_STATS_LEN; i += blockDim.x) s_acc[i] = 0;
   __syncthreads();
+  const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += stride) {
-    const int np = p.n_points[f];
-    const int tl = p.target_lane[f], el = p.ego_lane[f];
-    const uint32_t fl = p.flags[f];
-    atomicAdd(&s_acc[PP_STAT_FRAMES], 1ull);
-    atomicAdd(&s_acc[PP_STAT_POINTS], (unsigned long long)np);
-    if (tl >= 0 && tl < 3) atomicAdd(&s_acc[PP_STAT_TARGET_LANE0 + tl], 1ull);
-    if (el >= 0 && el < 3) atomicAdd(&s_acc[PP_STAT_EGO_LANE0 + el], 1ull);
-    if (tl != el) atomicAdd(&s_acc[PP_STAT_LANE_CHANGES], 1ull);
-    for (int b = 0; b < PP_NUM_FLAGS; b++)
-      if (fl & (1u << b)) atomicAdd(&s_acc[PP_STAT_FLAG0 + b], 1ull);
-    long long xs = 0;  // fixed-point (1/256 m) checksum: order-independent
-    for (int i = 0; i < np; i++) {
-      const double x = p.next_x[f * PP_PATH_LEN + i], y = p.next_y[f * PP_PATH_LEN + i];
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // pass 1: fixed-point (1/256 m) checksum of every emitted point: order-independent
+  long long xs = 0;
+  const int64_t total = n * PP_PATH_LEN;
+  for (int64_t e = tid; e < total; e += stride) {
+    const int64_t f = e / PP_PATH_LEN;
+    const int i = (int)(e - f * PP_PATH_LEN);
+    if (i < p.n_points[f]) {
+      const double x = p.next_x[e], y = p.next_y[e];
       if (x == x && y == y && fabs(x) < 1e12 && fabs(y) < 1e12)
         xs += (long long)(x * 256.0) + (long long)(y * 256.0);
     }
-    atomicAdd(&s_acc[PP_STAT_XSUM], (unsigned long long)xs);
+  }
+  const unsigned long long xw = warp_sum((unsigned long long)xs);
+  if (lane == 0 && xw) atomicAdd(&s_acc[PP_STAT_XSUM], xw);
+  // pass 2: per-frame counters.  Whole warps iterate together (ballots need every lane).
+  const int64_t n_round = (n + 31) / 32 * 32;
+  for (int64_t f = tid; f < n_round; f += stride) {
+    const bool live = f < n;
+    const int np = live ? p.n_points[f] : 0;
+    const int tl = live ? p.target_lane[f] : -1, el = live ? p.ego_lane[f] : -1;
+    const uint32_t fl = live ? p.flags[f] : 0u;
+    const unsigned long long pts = warp_sum((unsigned long long)np);
+    const unsigned m_live = __ballot_sync(0xffffffffu, live);
+    const unsigned m_chg = __ballot_sync(0xffffffffu, live && tl != el);
+    unsigned m_tl[3], m_el[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      m_tl[k] = __ballot_sync(0xffffffffu, tl == k);
+      m_el[k] = __ballot_sync(0xffffffffu, el == k);
+    }
+    // lane b counts flag bit b
+    unsigned my_flag = 0;
+#pragma unroll
+    for (int b = 0; b < PP_NUM_FLAGS; b++) {
+      const unsigned mb = __ballot_sync(0xffffffffu, (fl >> b) & 1u);
+      if (lane == b) my_flag = mb;
+    }
+    if (lane < PP_NUM_FLAGS && my_flag)
+      atomicAdd(&s_acc[PP_STAT_FLAG0 + lane], (unsigned long long)__popc(my_flag));
+    if (lane == 0) {
+      atomicAdd(&s_acc[PP_STAT_FRAMES], (unsigned long long)__popc(m_live));
+      atomicAdd(&s_acc[PP_STAT_POINTS], pts);
+      atomicAdd(&s_acc[PP_STAT_LANE_CHANGES], (unsigned long long)__popc(m_chg));
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        atomicAdd(&s_acc[PP_STAT_TARGET_LANE0 + k], (unsigned long long)__popc(m_tl[k]));
+        atomicAdd(&s_acc[PP_STAT_EGO_LANE0 + k], (unsigned long long)__popc(m_el[k]));
+      }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < PP_STATS_LEN; i += blockDim.x)
@@ -1107,8 +1149,8 @@ extern "C" int pp_stats_batch(const pp_plans *p, int64_t n_frames, int64_t *stat
   if (cudaMemsetAsync(stats_dev, 0, PP_STATS_LEN * sizeof(int64_t), st) != cudaSuccess)
     return check_launch("pp_stats_batch memset");
   if (n_frames == 0) return PP_OK;
-  int64_t want = (n_frames + 255) / 256;
-  int64_t cap = (int64_t)sm_count() * 4;
+  int64_t want = (n_frames * PP_PATH_LEN + 255) / 256;
+  int64_t cap = (int64_t)sm_count() * 8;
   int grid = (int)(want < cap ? want : cap);
   stats_kernel<<<grid, 256, 0, st>>>(*p, n_frames, (unsigned long long *)stats_dev);
   ppi::count_launch();
