@@ -745,15 +745,30 @@ stats_kernel(const __grid_constant__ pp_plans p, int64_t n, unsigned long long *
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  // pass 1: fixed-point (1/256 m) checksum of every emitted point: order-independent
+  // pass 1: fixed-point (1/256 m) checksum of every emitted point: order-independent.
+  // Four independent elements per trip and unconditional loads (the padding is valid memory,
+  // n_points only masks it afterwards) keep enough requests in flight to reach HBM speed.
   long long xs = 0;
   const int64_t total = n * PP_PATH_LEN;
-  for (int64_t e = tid; e < total; e += stride) {
-    const int64_t f = e / PP_PATH_LEN;
-    const int i = (int)(e - f * PP_PATH_LEN);
-    if (i < p.n_points[f]) {
-      const double x = p.next_x[e], y = p.next_y[e];
-      if (x == x && y == y && fabs(x) < 1e12 && fabs(y) < 1e12)
+  constexpr int kU = 4;
+  for (int64_t e0 = tid; e0 < total; e0 += stride * kU) {
+    double xv[kU], yv[kU];
+    int lim[kU], idx[kU];
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const int64_t e = e0 + u * stride;
+      const bool in = e < total;
+      const int64_t ec = in ? e : 0;
+      const int64_t f = ec / PP_PATH_LEN;
+      idx[u] = (int)(ec - f * PP_PATH_LEN);
+      xv[u] = p.next_x[ec];
+      yv[u] = p.next_y[ec];
+      lim[u] = in ? p.n_points[f] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const double x = xv[u], y = yv[u];
+      if (idx[u] < lim[u] && x == x && y == y && fabs(x) < 1e12 && fabs(y) < 1e12)
         xs += (long long)(x * 256.0) + (long long)(y * 256.0);
     }
   }

@@ -1,0 +1,31 @@
+"""profiles/traffic.json + per-kernel text summaries from an ncu --set full report.
+    python profiles/make_traffic.py gpurun_out/prof_r1d.ncu-rep r1d 262144
+"""
+import csv, io, json, os, re, subprocess, sys
+rep, tag, frames = sys.argv[1], sys.argv[2], int(sys.argv[3])
+here = os.path.dirname(os.path.abspath(__file__))
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units = rows[0], rows[1]
+col = {h: i for i, h in enumerate(hdr)}
+scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+def num(r, k):
+    return float(r[col[k]].replace(",", "") or 0)
+traffic, times = {}, {}
+for i, r in enumerate(rows[2:]):
+    name = re.search(r"(k_\w+|stats_kernel|plan_fused)", r[col["Kernel Name"]]).group(1)
+    rd = num(r, "dram__bytes_read.sum") * scale[units[col["dram__bytes_read.sum"]]]
+    wr = num(r, "dram__bytes_write.sum") * scale[units[col["dram__bytes_write.sum"]]]
+    traffic[name] = rd + wr
+    times[name] = num(r, "gpu__time_duration.sum")
+    txt = subprocess.run([sys.executable, os.path.join(here, "ncu_extract.py"), rep, str(i)],
+                         capture_output=True, text=True).stdout
+    open(os.path.join(here, f"{tag}_{name}_ncu.txt"), "w").write(txt)
+pipe = {k: v for k, v in traffic.items() if k != "stats_kernel"}
+json.dump({"source": f"profiles/{tag}_*_ncu.txt: ncu --set full --clock-control none, one launch of each "
+                     f"kernel over {frames} frames x 12 cars on a gpurun B200",
+           "frames_per_launch": frames, "dram_bytes_per_launch": pipe,
+           "stats_kernel_dram_bytes_per_launch": traffic.get("stats_kernel"),
+           "gpu_time_us_under_ncu": times},
+          open(os.path.join(here, "traffic.json"), "w"), indent=1)
+print(json.dumps(traffic), sum(pipe.values()) / frames, "B/frame")
