@@ -171,6 +171,42 @@ int pp_map_table(const pp_map *map, double *out) {
   return PP_OK;
 }
 
+#define PP_CK(call, what)                                           \
+  do {                                                              \
+    cudaError_t e_ = (call);                                        \
+    if (e_ != cudaSuccess) {                                        \
+      ppi::set_cuda_error(what, (int)e_, cudaGetErrorString(e_));   \
+      cudaGetLastError();                                           \
+      return PP_E_CUDA;                                             \
+    }                                                               \
+  } while (0)
+
+int pp_dev_alloc(void **out, size_t bytes) {
+  if (!out) return PP_E_ARG;
+  *out = nullptr;
+  PP_CK(cudaMalloc(out, bytes ? bytes : 1), "pp_dev_alloc");
+  return PP_OK;
+}
+int pp_dev_free(void *p) {
+  if (p) PP_CK(cudaFree(p), "pp_dev_free");
+  return PP_OK;
+}
+int pp_dev_upload(void *dst_dev, const void *src_host, size_t bytes) {
+  if (bytes && (!dst_dev || !src_host)) return PP_E_ARG;
+  if (bytes) PP_CK(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice), "pp_dev_upload");
+  return PP_OK;
+}
+int pp_dev_download(void *dst_host, const void *src_dev, size_t bytes) {
+  if (bytes && (!dst_host || !src_dev)) return PP_E_ARG;
+  if (bytes)
+    PP_CK(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost), "pp_dev_download");
+  return PP_OK;
+}
+int pp_dev_sync(void) {
+  PP_CK(cudaDeviceSynchronize(), "pp_dev_sync");
+  return PP_OK;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------

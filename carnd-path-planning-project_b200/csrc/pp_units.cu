@@ -237,6 +237,45 @@ __global__ void k_selftest_math(int64_t n, unsigned long long seed, unsigned lon
   atomicMax(&counts[3], (unsigned long long)d);
 }
 
+__global__ void k_project_speed(const double *table, int n_wp, const double *vx, const double *vy,
+                                const int32_t *next_wp, double *ovs, double *ovd, int64_t n) {
+  extern __shared__ __align__(16) double s_map[];
+  const MapView m = stage_map(s_map, table, n_wp);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a, b;
+  project_speed(m, vx[i], vy[i], next_wp[i], a, b);
+  ovs[i] = a;
+  ovd[i] = b;
+}
+
+__global__ void k_speed_controller(int op, const __grid_constant__ pp_config cfg, const double *start,
+                                   double *target, double *time, double *shift, const double *a,
+                                   const double *b, double *out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  SpeedCtl c;
+  c.start = start[i];
+  c.target = target[i];
+  c.time = time[i];
+  c.shift = shift[i];
+  if (op == 3) {
+    sc_init(c, cfg, start[i]);
+    target[i] = c.target;
+    time[i] = c.time;
+    shift[i] = c.shift;
+  } else if (op == 0) {
+    out[i] = sc_speed(c, a[i]);
+  } else if (op == 1) {
+    sc_limit(c, a[i], b[i]);
+    target[i] = c.target;
+    time[i] = c.time;
+  } else {
+    sc_override(c, a[i], b[i]);
+    shift[i] = c.shift;
+  }
+}
+
 int finish(const char *what) {
   ppi::count_launch();
   cudaError_t e = cudaGetLastError();
@@ -377,6 +416,33 @@ int pp_trajectory_build_batch(const pp_map *map, const pp_config *cfg, const int
       map->dev_table, map->n, *cfg, prev_n, prev_x, prev_y, ego_x, ego_y, ego_yaw_deg, target_lane,
       ego_d, ego_vd, sc_start, sc_target, sc_time, out_x, out_y, out_n, out_flags, n);
   return finish("k_trajectory");
+}
+
+int pp_project_speed_batch(const pp_map *map, const double *vx, const double *vy,
+                           const int32_t *next_wp, double *out_vs, double *out_vd, int64_t n,
+                           void *stream) {
+  if (!vx || !vy || !next_wp || !out_vs || !out_vd || n < 0) return PP_E_ARG;
+  int rc = need_map(map, "pp_project_speed_batch");
+  if (rc != PP_OK) return rc;
+  if (n == 0) return PP_OK;
+  k_project_speed<<<grid_for(n), kB, map_smem(map), (cudaStream_t)stream>>>(
+      map->dev_table, map->n, vx, vy, next_wp, out_vs, out_vd, n);
+  return finish("k_project_speed");
+}
+
+int pp_speed_controller_batch(int32_t op, const double *start, double *target, double *time,
+                              double *shift, const double *a, const double *b, double *out,
+                              int64_t n, void *stream) {
+  if (op < 0 || op > 3 || !start || !target || !time || !shift || n < 0) return PP_E_ARG;
+  if (op != 3 && !a) return PP_E_ARG;
+  if (op == 0 && !out) return PP_E_ARG;
+  if ((op == 1 || op == 2) && !b) return PP_E_ARG;
+  if (n == 0) return PP_OK;
+  pp_config cfg;
+  pp_config_default(&cfg);
+  k_speed_controller<<<grid_for(n), kB, 0, (cudaStream_t)stream>>>(op, cfg, start, target, time,
+                                                                   shift, a, b, out, n);
+  return finish("k_speed_controller");
 }
 
 int pp_selftest_math(int64_t n, uint64_t seed, int64_t *counts_dev, void *stream) {

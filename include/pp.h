@@ -30,6 +30,7 @@
 #ifndef PP_B200_H
 #define PP_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -237,6 +238,13 @@ int pp_lane_matching_batch(const pp_map *map, const double *rx, const double *ry
                            int32_t *out_next_wp, double *out_s, double *out_d,
                            double *out_vs, double *out_vd, int64_t n, void *cuda_stream);
 
+/* Map::project_speed (src/main.cpp:330-358) alone: speed vectors (vx, vy)[n]
+ * against the reference-line segment ending at waypoint next_wp[n] (un-wrapped
+ * ids as lane_matching returns them): out_vs, out_vd [n]. */
+int pp_project_speed_batch(const pp_map *map, const double *vx, const double *vy,
+                           const int32_t *next_wp, double *out_vs, double *out_vd, int64_t n,
+                           void *cuda_stream);
+
 /* Map::get_lane_pos (src/main.cpp:277-328) relative to (rx, ry):
  * out_x, out_y, out_dist [n]; out_wp [n]. */
 int pp_get_lane_pos_batch(const pp_map *map, const double *rx, const double *ry,
@@ -299,6 +307,26 @@ int pp_trajectory_build_batch(const pp_map *map, const pp_config *cfg, const int
                               const double *sc_target, const double *sc_time, double *out_x,
                               double *out_y, int32_t *out_n, uint32_t *out_flags, int64_t n,
                               void *cuda_stream);
+
+/* SpeedController (src/main.cpp:488-548) on n explicit controllers
+ * (start, target, time, shift [n], all read; target/time/shift may be rewritten):
+ *   op 0  get_speed(a)                 -> out[n]            (:503-512)
+ *   op 1  add_limit_breakpoint(a, b)   -> target, time      (:513-533)
+ *   op 2  override_speed(a, b)         -> shift             (:534-547)
+ *   op 3  SpeedController(start)       -> target, time, shift (:493-501; a, b unused)
+ * a, b [n] are the method's arguments; out may be NULL for ops 1-3, a/b for op 3. */
+int pp_speed_controller_batch(int32_t op, const double *start, double *target, double *time,
+                              double *shift, const double *a, const double *b, double *out,
+                              int64_t n, void *cuda_stream);
+
+/* Device-memory helpers, so that a caller (and include/pp.hpp) needs neither
+ * the CUDA headers nor libcudart of its own: plain cudaMalloc / cudaFree /
+ * cudaMemcpy (synchronous) / cudaDeviceSynchronize on the current device. */
+int pp_dev_alloc(void **out, size_t bytes);
+int pp_dev_free(void *p);
+int pp_dev_upload(void *dst_dev, const void *src_host, size_t bytes);
+int pp_dev_download(void *dst_host, const void *src_dev, size_t bytes);
+int pp_dev_sync(void);
 
 /* Device self-test of the exact-arithmetic helpers the kernels use in place of
  * generic divisions / fmod / atan2 (Markstein quotient with cached reciprocal,
