@@ -1,27 +1,34 @@
 // pp_plan.cu — the planning kernels and pp_plan_batch / pp_stats_batch.
 //
-// What bounds this path is the FP64 pipe, not HBM (1,520
-// algorithmic bytes against ~35-45 k FP64-heavy instructions per frame), and
-// most of those instructions sit in serial recurrences.  So every LANE carries
-// its own independent recurrence, and the step is cut into phases so that each
-// phase runs with the mapping that keeps its lanes converged:
+// What bounds this path is FP64 instruction issue and branch divergence, not HBM
+// (1,520 algorithmic bytes against ~35 k FP64-heavy instructions
+// per frame), and most of those instructions sit in serial recurrences.  So
+// every LANE carries its own independent recurrence, and the step is cut into
+// phases so that each phase runs with the mapping that keeps its lanes
+// converged and its register / code footprint small:
 //
 //   k_prep     one thread per FRAME : ego state (src/main.cpp:1254-1282),
 //              closest-waypoint scan + reference segment (:143-197), ego lane
 //              matching + speed projection (:1302-1313)
 //   k_cars     one thread per CAR   : Map::lane_matching + project_speed for
-//              every sensor-fusion object (:1325-1350) — 12x more parallel
-//              work items than frames, coalesced loads/stores
-//   k_plan     one thread per FRAME : LaneChangePlanner reductions, veto,
-//              followed cars, LimitSpeed, SpeedController (:1352-1438) and
-//              TrajectoryBuilder::build (:1446-1448, spline fit + emission)
+//              every sensor-fusion object (:1325-1350); warp tiles of 256 cars
+//              counting-sorted by expected walk length
+//   k_decide   one thread per FRAME : LaneChangePlanner reductions, veto,
+//              followed cars, LimitSpeed, SpeedController (:1352-1438),
+//              TrajectoryBuilder set-up and the tk::spline fit (:565-904)
+//   k_emit     one thread per FRAME : the 0.02 s point emission loop
+//              (:904-1040) on the <= 7 reachable knots staged in shared memory
+//   k_fallback dense, side stream   : the angle-based generator (:848-901) for
+//              the frames k_decide queued (~0.4 %)
+//   k_slow     warp per frame, side : the complete path for frames k_emit gave
+//              up on (headings / rotations outside its fast forms, ~0.03 %)
 //
 // The few hundred bytes per frame that cross between phases go through a
-// stream-ordered scratch buffer in HBM (≈ 0.6 GB per 1M frames, ≈ 0.3 ms of
-// the ~10 ms step).  The ncu evidence that led here (the single fused kernel:
-// 45 % instruction-fetch stalls on 155 KB of SASS, 15 of 32 lanes active,
-// 51 % of warp instructions in the per-car walks at ~10 lanes) is in
-// profiles/r1_v0_*.  The fused single-kernel form is kept as variant 1: it
+// double-buffered, stream-ordered scratch in HBM.  The ncu evidence behind each
+// cut is in profiles/ (r1_v0: the single fused kernel, 45 % instruction-fetch
+// stalls on 155 KB of SASS at 15 of 32 lanes; r1b/r1c: the division of the
+// interior step at 4 lanes, the library atan2 at 3.6 lanes, knot staging; r1d:
+// the current state).  The fused single-kernel form is kept as variant 1: it
 // has the lowest latency for small batches and is the bitwise cross-check of
 // the pipeline (tests/test_gpu_parity.py).
 #include <cuda_runtime.h>
