@@ -112,6 +112,63 @@ def run_reference(args):
     return 0
 
 
+def run_rollouts(args):
+    """BASELINE configs[2]: closed-loop rollouts, device-resident simulator + planner.
+    One step = --ticks ticks of every rollout; value = ego-frames (rollout-ticks) per second."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from __graft_entry__ import load_package
+    pp = load_package()
+    m = pp.Map()
+    n, ticks = args.rollouts, args.ticks
+    ro = pp.Rollouts(m, n, N_CARS, seed=SEED, first=rank * n)
+    ro.run(max(3, min(20, ticks)), args.consume_k)  # warm-up ticks (also leaves the cold start)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = pp.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(1, args.steps if args.steps != 50 else 1)
+    ev0.record()
+    for _ in range(steps):
+        ro.run(ticks, args.consume_k)
+    st = ro.stats()
+    if world > 1:
+        dist.all_reduce(st)
+    ev1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    if rank == 0:
+        stats = st.cpu().numpy()
+        line = {"metric": "closed-loop ego-frames/sec (rollout-ticks)",
+                "value": world * n * ticks * steps / (ms * 1e-3), "unit": "frames/s",
+                "n_gpus": world, "steps": steps, "warmup": 3, "ms_per_step": ms / steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"configs[2]: {n} closed-loop rollouts x {ticks} ticks per GPU, "
+                                       f"{N_CARS} cars, consume_k={args.consume_k}",
+                           "ms_per_tick": ms / steps / ticks},
+                "gpu_launches": int(pp.launch_count() - launches0), "clocks": clocks,
+                "stats": {"frames": int(stats[0]), "points": int(stats[1]),
+                          "lane_changes": int(stats[8])}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 class ClockSampler:
     """SM clock + throttle reasons sampled every ~5 ms through NVML on a thread while the
     timed region runs (nvidia-smi's own loop is too coarse for a sub-second region)."""
@@ -182,9 +239,17 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--workload", default="frames", choices=["frames", "rollouts"],
+                    help="frames = BASELINE configs[1] (the headline metric, default); "
+                         "rollouts = configs[2], closed-loop rollouts (secondary line)")
+    ap.add_argument("--rollouts", type=int, default=65536, help="rollouts per GPU")
+    ap.add_argument("--ticks", type=int, default=1000)
+    ap.add_argument("--consume-k", type=int, default=1)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "rollouts":
+        return run_rollouts(args)
     args.warmup = max(args.warmup, 3)
 
     import numpy as np

@@ -37,6 +37,8 @@ EXPORTS = [
     "pp_set_phase_timing", "pp_get_phase_ms", "pp_speed_controller_batch",
     "pp_project_speed_batch",
     "pp_dev_alloc", "pp_dev_free", "pp_dev_upload", "pp_dev_download", "pp_dev_sync",
+    "pp_rollouts_create", "pp_rollouts_destroy", "pp_rollouts_run", "pp_rollouts_last",
+    "pp_rollouts_get_state", "pp_rollouts_stats",
 ]
 
 
@@ -234,3 +236,83 @@ def stats_batch(plans: DevicePlans, stream=None):
     _check(lib.pp_stats_batch(C.byref(ps), C.c_int64(plans.n), C.c_void_p(out.data_ptr()),
                               C.c_void_p(stream)), "pp_stats_batch")
     return out
+
+
+class RolloutStateHost:
+    """Host copy of the simulator state of a Rollouts object (numpy arrays)."""
+
+    def __init__(self, n: int, n_cars: int):
+        self.n, self.n_cars, self.tick = n, n_cars, 0
+        for name, dt, kind in abi.ROLLOUT_STATE_FIELDS:
+            inner = {0: (), "path": (abi.PATH_LEN,), "cars": (n_cars,)}[kind]
+            setattr(self, name, np.zeros((n,) + inner, dtype=dt))
+
+    def struct(self) -> abi.RolloutState:
+        s = abi.RolloutState()
+        for name, _, _ in abi.ROLLOUT_STATE_FIELDS:
+            setattr(s, name, getattr(self, name).ctypes.data)
+        s.tick = self.tick
+        return s
+
+
+class Rollouts:
+    """Closed-loop rollouts (BASELINE config 3): pp_rollouts_* of include/pp.h."""
+
+    def __init__(self, m: Map, n: int, n_cars: int = 12, seed: int = 0x5EED, first: int = 0):
+        self.map, self.n, self.n_cars = m, n, n_cars
+        self._h = C.c_void_p()
+        _check(lib.pp_rollouts_create(m.handle, C.c_int64(n), C.c_int32(n_cars), C.c_uint64(seed),
+                                      C.c_int64(first), C.byref(self._h)), "pp_rollouts_create")
+
+    def run(self, ticks: int, consume_k: int = 1, cfg: Config | None = None, stream=None):
+        import torch
+        cfg = cfg or default_config()
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        _check(lib.pp_rollouts_run(self._h, C.byref(cfg), C.c_int64(ticks), C.c_int32(consume_k),
+                                   C.c_void_p(stream)), "pp_rollouts_run")
+
+    def state(self) -> RolloutStateHost:
+        st = RolloutStateHost(self.n, self.n_cars)
+        s = st.struct()
+        _check(lib.pp_rollouts_get_state(self._h, C.byref(s)), "pp_rollouts_get_state")
+        st.tick = int(s.tick)
+        return st
+
+    def last(self):
+        """(FrameBatch, PlanBatch) of the last tick, copied to the host."""
+        import torch
+        fs, ps = Frames(), Plans()
+        _check(lib.pp_rollouts_last(self._h, C.byref(fs), C.byref(ps)), "pp_rollouts_last")
+        torch.cuda.synchronize()
+        mc = max(self.n_cars, 1)
+        fb = FrameBatch(self.n, mc)
+        for name, arr in fb.arrays().items():
+            _check(lib.pp_dev_download(C.c_void_p(arr.ctypes.data), C.c_void_p(getattr(fs, name)),
+                                       C.c_size_t(arr.nbytes)), "pp_dev_download")
+        pb = PlanBatch(self.n, mc, diag=True, cars=True)
+        for name, _, _ in abi.PLAN_FIELDS:
+            arr = getattr(pb, name)
+            _check(lib.pp_dev_download(C.c_void_p(arr.ctypes.data), C.c_void_p(getattr(ps, name)),
+                                       C.c_size_t(arr.nbytes)), "pp_dev_download")
+        return fb, pb
+
+    def stats(self, stream=None):
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        out = torch.zeros(STATS_LEN, dtype=torch.int64, device="cuda")
+        _check(lib.pp_rollouts_stats(self._h, C.c_void_p(out.data_ptr()), C.c_void_p(stream)),
+               "pp_rollouts_stats")
+        return out
+
+    def close(self):
+        if self._h:
+            lib.pp_rollouts_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

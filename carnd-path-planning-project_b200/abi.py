@@ -111,6 +111,19 @@ class Plans(C.Structure):
     _fields_ = [(n, _dp) for n, _, _ in PLAN_FIELDS]
 
 
+ROLLOUT_STATE_FIELDS = [  # (name, dtype, inner) ; inner: 0 scalar, 'path', 'cars'
+    ("ego_x", np.float64, 0), ("ego_y", np.float64, 0), ("ego_yaw_deg", np.float64, 0),
+    ("ego_speed_mph", np.float64, 0), ("path_n", np.int32, 0), ("path_x", np.float64, "path"),
+    ("path_y", np.float64, "path"), ("target_lane", np.int32, 0), ("car_lane", np.int32, "cars"),
+    ("car_wp", np.int32, "cars"), ("car_ratio", np.float64, "cars"),
+    ("car_speed", np.float64, "cars"),
+]
+
+
+class RolloutState(C.Structure):
+    _fields_ = [(n, _dp) for n, _, _ in ROLLOUT_STATE_FIELDS] + [("tick", C.c_int64)]
+
+
 def default_config() -> Config:
     """The literals of reference src/main.cpp:30,39-49 (also what
     pp_config_default writes; tests check the two agree)."""

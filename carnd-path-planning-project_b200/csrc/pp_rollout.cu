@@ -1,0 +1,448 @@
+// pp_rollout.cu — closed-loop rollouts (BASELINE config 3): a device-resident
+// simulator model around pp_plan_batch.  The model is specified in include/pp.h
+// (pp_rollouts); every operation in it is + - * / (and one sqrt) so that the CPU
+// restatement the tests check it against is bit-identical.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "pp_internal.h"
+
+struct pp_rollouts {
+  const pp_map *map = nullptr;
+  int64_t n = 0;   // rollouts
+  int32_t c = 0;   // cars per rollout
+  uint64_t seed = 0;
+  int64_t first = 0;
+  int64_t tick = 0;
+  char *buf = nullptr;  // one device allocation
+  // simulator state
+  double *ego_x, *ego_y, *ego_yaw, *ego_mph, *path_x, *path_y, *car_ratio, *car_speed;
+  int32_t *path_n, *target_lane, *car_lane, *car_wp;
+  // per-tick frames and plans
+  pp_frames fr;
+  pp_plans pl;
+  int64_t *stats_tick, *stats_sum;
+};
+
+namespace {
+
+constexpr int kB = 128;
+constexpr double kTick = 0.02;
+
+// splitmix64, as in pp_synth.cpp
+__host__ __device__ inline uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ inline double u01(uint64_t v) {
+  return (double)(v >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// The map as the simulator sees it: rows of PP_MAP_STRIDE doubles, index wrapped into [0, n).
+struct Track {
+  const double *t;  // row 0
+  int n;
+  int stride;
+  __host__ __device__ const double *row(int i) const {
+    int k = i % n;
+    if (k < 0) k += n;
+    return t + (size_t)k * stride;
+  }
+  __host__ __device__ double len(int w, int lane) const { return row(w)[10 + lane]; }
+  // walk ds metres along lane `lane` from (w, u)
+  __host__ __device__ void walk(int &w, double &u, int lane, double ds) const {
+    for (int guard = 0; guard < 4 * n; guard++) {
+      const double l = len(w, lane);
+      if (ds >= 0) {
+        const double rem = l * (1 - u);
+        if (ds <= rem) {
+          u += ds / l;
+          break;
+        }
+        ds -= rem;
+        u = 0;
+        w++;
+      } else {
+        const double rem = l * u;
+        if (-ds <= rem) {
+          u += ds / l;
+          break;
+        }
+        ds += rem;
+        u = 1;
+        w--;
+      }
+    }
+    w %= n;
+    if (w < 0) w += n;
+  }
+  // position and velocity of a car at (lane, w, u) moving at v
+  __host__ __device__ void car(int lane, int w, double u, double v, double &x, double &y,
+                               double &vx, double &vy) const {
+    const double *a = row(w - 1), *b = row(w);
+    const double ax = a[2 + 2 * lane], ay = a[3 + 2 * lane];
+    const double bx = b[2 + 2 * lane], by = b[3 + 2 * lane];
+    const double l = b[10 + lane];
+    x = ax + (bx - ax) * u;
+    y = ay + (by - ay) * u;
+    const double tx = (bx - ax) / l, ty = (by - ay) / l;
+    vx = v * tx;
+    vy = v * ty;
+  }
+};
+
+// frame <- state (one thread per rollout)
+__global__ void __launch_bounds__(kB)
+k_sim_frames(Track trk, int64_t n, int c, const double *ego_x, const double *ego_y,
+             const double *ego_yaw, const double *ego_mph, const int32_t *path_n,
+             const double *path_x, const double *path_y, const int32_t *target_lane,
+             const int32_t *car_lane, const int32_t *car_wp, const double *car_ratio,
+             const double *car_speed, pp_frames fr) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const_cast<double *>(fr.ego_x)[r] = ego_x[r];
+  const_cast<double *>(fr.ego_y)[r] = ego_y[r];
+  const_cast<double *>(fr.ego_yaw_deg)[r] = ego_yaw[r];
+  const_cast<double *>(fr.ego_speed_mph)[r] = ego_mph[r];
+  const int pn = path_n[r];
+  const_cast<int32_t *>(fr.prev_n)[r] = pn;
+  for (int i = 0; i < PP_PREV_KEEP; i++) {
+    const bool have = i < pn;
+    const_cast<double *>(fr.prev_x)[r * PP_PREV_KEEP + i] = have ? path_x[r * PP_PATH_LEN + i] : 0.0;
+    const_cast<double *>(fr.prev_y)[r * PP_PREV_KEEP + i] = have ? path_y[r * PP_PATH_LEN + i] : 0.0;
+  }
+  const_cast<int32_t *>(fr.target_lane_in)[r] = target_lane[r];
+  const_cast<int32_t *>(fr.n_cars)[r] = c;
+  for (int j = 0; j < c; j++) {
+    const int64_t k = r * c + j;
+    double x, y, vx, vy;
+    trk.car(car_lane[k], car_wp[k], car_ratio[k], car_speed[k], x, y, vx, vy);
+    const_cast<int32_t *>(fr.car_id)[k] = j;
+    const_cast<double *>(fr.car_x)[k] = x;
+    const_cast<double *>(fr.car_y)[k] = y;
+    const_cast<double *>(fr.car_vx)[k] = vx;
+    const_cast<double *>(fr.car_vy)[k] = vy;
+  }
+}
+
+// state <- simulator step(plan) (one thread per rollout)
+__global__ void __launch_bounds__(kB)
+k_sim_advance(Track trk, int64_t n, int c, uint64_t seed, int64_t first, int64_t tick, int consume_k,
+              double *ego_x, double *ego_y, double *ego_mph, int32_t *path_n, double *path_x,
+              double *path_y, int32_t *target_lane, int32_t *car_lane, int32_t *car_wp,
+              double *car_ratio, double *car_speed, pp_plans pl) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  // ---- the ego consumes k points of the new trajectory
+  const int np = pl.n_points[r];
+  const int k = consume_k < np ? consume_k : np;
+  const double *nx = pl.next_x + r * PP_PATH_LEN, *ny = pl.next_y + r * PP_PATH_LEN;
+  if (k > 0) {
+    const double ox = ego_x[r], oy = ego_y[r];
+    const double qx = nx[k - 1], qy = ny[k - 1];
+    const double d = sqrt((qx - ox) * (qx - ox) + (qy - oy) * (qy - oy));
+    ego_x[r] = qx;
+    ego_y[r] = qy;
+    ego_mph[r] = d / (kTick * k) * 2.237;
+  }
+  for (int i = 0; i < PP_PATH_LEN; i++) {
+    const bool have = i + k < np;
+    path_x[r * PP_PATH_LEN + i] = have ? nx[i + k] : 0.0;
+    path_y[r * PP_PATH_LEN + i] = have ? ny[i + k] : 0.0;
+  }
+  path_n[r] = np - k;
+  target_lane[r] = pl.target_lane[r];
+  // ---- traffic
+  const double dt = kTick * (k > 0 ? k : 1);
+  const int ref_wp = pl.ref_wp[r];
+  for (int j = 0; j < c; j++) {
+    const int64_t q = r * c + j;
+    int lane = car_lane[q], w = car_wp[q];
+    double u = car_ratio[q], v = car_speed[q];
+    const int m_lane = pl.car_lane[q];
+    const double m_s = pl.car_s[q];
+    if (m_lane < 0 || m_s < -100.0 || m_s > 300.0) {  // respawn
+      const uint64_t key = mix64(mix64(seed ^ 0x5157ull) ^ ((uint64_t)(first + r) * 0xD1B54A32D192ED03ull));
+      const uint64_t h = mix64(key ^ ((uint64_t)tick * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)j << 48));
+      const double u1 = u01(mix64(h + 1)), u2 = u01(mix64(h + 2)), u3 = u01(mix64(h + 3));
+      const double ds = (m_lane >= 0 && m_s < -100.0) ? 200.0 + 100.0 * u1 : -(60.0 + 40.0 * u1);
+      lane = (int)(3.0 * u2);
+      if (lane > 2) lane = 2;
+      v = 17.88 + 8.94 * u3;
+      w = ref_wp;
+      u = 0.5;
+      trk.walk(w, u, lane, ds);
+    } else {  // constant speed along the lane centre line
+      u += (v * dt) / trk.len(w, lane);
+      for (int guard = 0; guard < 64 && u >= 1; guard++) {
+        const double left = (u - 1) * trk.len(w, lane);
+        w = w + 1 == trk.n ? 0 : w + 1;
+        u = left / trk.len(w, lane);
+      }
+    }
+    car_lane[q] = lane;
+    car_wp[q] = w;
+    car_ratio[q] = u;
+    car_speed[q] = v;
+  }
+}
+
+__global__ void k_add_stats(int64_t *sum, const int64_t *tick) {
+  const int i = threadIdx.x;
+  if (i < PP_STATS_LEN) sum[i] += tick[i];
+}
+
+inline size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int cuda_fail(const char *what, cudaError_t e) {
+  ppi::set_cuda_error(what, (int)e, cudaGetErrorString(e));
+  cudaGetLastError();
+  return PP_E_CUDA;
+}
+
+}  // namespace
+
+extern "C" int pp_rollouts_create(const pp_map *map, int64_t n, int32_t c, uint64_t seed,
+                                  int64_t first, pp_rollouts **out) {
+  if (!out) return PP_E_ARG;
+  *out = nullptr;
+  if (!map || n <= 0 || c < 0 || c > PP_MAX_CARS) return PP_E_ARG;
+  if (!map->dev_table) {
+    ppi::set_cuda_error("pp_rollouts_create: map has no device table (no usable CUDA device)", 0, "");
+    return PP_E_CUDA;
+  }
+  pp_rollouts *r = new (std::nothrow) pp_rollouts();
+  if (!r) return PP_E_NOMEM;
+  r->map = map;
+  r->n = n;
+  r->c = c;
+  r->seed = seed;
+  r->first = first;
+  const size_t N = (size_t)n, NC = (size_t)n * (size_t)(c > 0 ? c : 1);
+  // carve one allocation
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off += al(bytes);
+    return o;
+  };
+  const size_t o_ex = take(N * 8), o_ey = take(N * 8), o_yaw = take(N * 8), o_mph = take(N * 8);
+  const size_t o_pn = take(N * 4), o_px = take(N * PP_PATH_LEN * 8), o_py = take(N * PP_PATH_LEN * 8);
+  const size_t o_tl = take(N * 4), o_cl = take(NC * 4), o_cw = take(NC * 4), o_cr = take(NC * 8),
+               o_cs = take(NC * 8);
+  // frames
+  const size_t f_ex = take(N * 8), f_ey = take(N * 8), f_yaw = take(N * 8), f_mph = take(N * 8),
+               f_pn = take(N * 4), f_px = take(N * PP_PREV_KEEP * 8), f_py = take(N * PP_PREV_KEEP * 8),
+               f_tl = take(N * 4), f_nc = take(N * 4), f_id = take(NC * 4), f_cx = take(NC * 8),
+               f_cy = take(NC * 8), f_vx = take(NC * 8), f_vy = take(NC * 8);
+  // plans (all outputs: tests compare them tick by tick)
+  const size_t p_nx = take(N * PP_PATH_LEN * 8), p_ny = take(N * PP_PATH_LEN * 8), p_np = take(N * 4),
+               p_el = take(N * 4), p_rw = take(N * 4), p_tl = take(N * 4), p_fl = take(N * 4);
+  size_t p_d[8];
+  for (int i = 0; i < 8; i++) p_d[i] = take(N * 8);
+  const size_t p_i0 = take(N * 4), p_i1 = take(N * 4);
+  const size_t p_cs = take(NC * 8), p_cd = take(NC * 8), p_cvs = take(NC * 8), p_cvd = take(NC * 8),
+               p_cl = take(NC * 4), p_cw = take(NC * 4);
+  const size_t o_st = take(PP_STATS_LEN * 8), o_ss = take(PP_STATS_LEN * 8);
+  cudaError_t e = cudaMalloc((void **)&r->buf, off);
+  if (e != cudaSuccess) {
+    delete r;
+    return cuda_fail("cudaMalloc(rollouts)", e);
+  }
+  cudaMemset(r->buf, 0, off);
+  char *b = r->buf;
+  r->ego_x = (double *)(b + o_ex);
+  r->ego_y = (double *)(b + o_ey);
+  r->ego_yaw = (double *)(b + o_yaw);
+  r->ego_mph = (double *)(b + o_mph);
+  r->path_n = (int32_t *)(b + o_pn);
+  r->path_x = (double *)(b + o_px);
+  r->path_y = (double *)(b + o_py);
+  r->target_lane = (int32_t *)(b + o_tl);
+  r->car_lane = (int32_t *)(b + o_cl);
+  r->car_wp = (int32_t *)(b + o_cw);
+  r->car_ratio = (double *)(b + o_cr);
+  r->car_speed = (double *)(b + o_cs);
+  pp_frames &f = r->fr;
+  f.ego_x = (double *)(b + f_ex);
+  f.ego_y = (double *)(b + f_ey);
+  f.ego_yaw_deg = (double *)(b + f_yaw);
+  f.ego_speed_mph = (double *)(b + f_mph);
+  f.prev_n = (int32_t *)(b + f_pn);
+  f.prev_x = (double *)(b + f_px);
+  f.prev_y = (double *)(b + f_py);
+  f.target_lane_in = (int32_t *)(b + f_tl);
+  f.n_cars = (int32_t *)(b + f_nc);
+  f.car_id = (int32_t *)(b + f_id);
+  f.car_x = (double *)(b + f_cx);
+  f.car_y = (double *)(b + f_cy);
+  f.car_vx = (double *)(b + f_vx);
+  f.car_vy = (double *)(b + f_vy);
+  f.max_cars = c > 0 ? c : 1;
+  f.reserved = 0;
+  pp_plans &p = r->pl;
+  p.next_x = (double *)(b + p_nx);
+  p.next_y = (double *)(b + p_ny);
+  p.n_points = (int32_t *)(b + p_np);
+  p.ego_lane = (int32_t *)(b + p_el);
+  p.ref_wp = (int32_t *)(b + p_rw);
+  p.target_lane = (int32_t *)(b + p_tl);
+  p.flags = (uint32_t *)(b + p_fl);
+  p.ego_s = (double *)(b + p_d[0]);
+  p.ego_d = (double *)(b + p_d[1]);
+  p.ego_vs = (double *)(b + p_d[2]);
+  p.ego_vd = (double *)(b + p_d[3]);
+  p.ego_speed = (double *)(b + p_d[4]);
+  p.ego_acc = (double *)(b + p_d[5]);
+  p.target_speed = (double *)(b + p_d[6]);
+  p.target_time = (double *)(b + p_d[7]);
+  p.next_car_id = (int32_t *)(b + p_i0);
+  p.next_car_in_target_lane = (int32_t *)(b + p_i1);
+  p.car_s = (double *)(b + p_cs);
+  p.car_d = (double *)(b + p_cd);
+  p.car_vs = (double *)(b + p_cvs);
+  p.car_vd = (double *)(b + p_cvd);
+  p.car_lane = (int32_t *)(b + p_cl);
+  p.car_next_wp = (int32_t *)(b + p_cw);
+  r->stats_tick = (int64_t *)(b + o_st);
+  r->stats_sum = (int64_t *)(b + o_ss);
+
+  // ---- initial state on the host: a pure function of (seed, first + r)
+  std::vector<double> ex(N), ey(N), yaw(N), mph(N), cr(NC), cs(NC);
+  std::vector<int32_t> tl(N), cl(NC), cw(NC);
+  Track trk{map->table.data(), map->n, PP_MAP_STRIDE};
+  for (int64_t i = 0; i < n; i++) {
+    uint64_t key = mix64(mix64(seed ^ 0x1417ull) ^ ((uint64_t)(first + i) * 0xD1B54A32D192ED03ull));
+    uint64_t ctr = 0;
+    auto uni = [&]() { return u01(mix64(key + (ctr++) * 0x9E3779B97F4A7C15ull)); };
+    int w = (int)(uni() * map->n);
+    if (w >= map->n) w = map->n - 1;
+    double u = uni();
+    int lane = (int)(uni() * 3);
+    if (lane > 2) lane = 2;
+    double x, y, vx, vy;
+    trk.car(lane, w, u, 1.0, x, y, vx, vy);
+    ex[i] = x;
+    ey[i] = y;
+    yaw[i] = std::atan2(vy, vx) * 180 / M_PI;
+    mph[i] = 0.0;
+    tl[i] = lane;
+    for (int j = 0; j < c; j++) {
+      int l = (int)(uni() * 3);
+      if (l > 2) l = 2;
+      const double ds = -100.0 + 400.0 * uni();
+      const double sp = 17.88 + 8.94 * uni();
+      int ww = w;
+      double uu = u;
+      trk.walk(ww, uu, l, ds);
+      cl[i * c + j] = l;
+      cw[i * c + j] = ww;
+      cr[i * c + j] = uu;
+      cs[i * c + j] = sp;
+    }
+  }
+  bool ok = true;
+  auto up = [&](void *dst, const void *src, size_t bytes) {
+    if (bytes && cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+  };
+  up(r->ego_x, ex.data(), N * 8);
+  up(r->ego_y, ey.data(), N * 8);
+  up(r->ego_yaw, yaw.data(), N * 8);
+  up(r->ego_mph, mph.data(), N * 8);
+  up(r->target_lane, tl.data(), N * 4);
+  if (c > 0) {
+    up(r->car_lane, cl.data(), NC * 4);
+    up(r->car_wp, cw.data(), NC * 4);
+    up(r->car_ratio, cr.data(), NC * 8);
+    up(r->car_speed, cs.data(), NC * 8);
+  }
+  if (!ok) {
+    cudaError_t e2 = cudaGetLastError();
+    cudaFree(r->buf);
+    delete r;
+    return cuda_fail("cudaMemcpy(rollouts init)", e2);
+  }
+  *out = r;
+  return PP_OK;
+}
+
+extern "C" void pp_rollouts_destroy(pp_rollouts *r) {
+  if (!r) return;
+  if (r->buf) cudaFree(r->buf);
+  delete r;
+}
+
+extern "C" int pp_rollouts_run(pp_rollouts *r, const pp_config *cfg, int64_t n_ticks,
+                               int32_t consume_k, void *cuda_stream) {
+  if (!r || !cfg || n_ticks < 0 || consume_k < 1 || consume_k > PP_PATH_LEN - PP_PREV_KEEP)
+    return PP_E_ARG;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  // device rows of the padded table: logical row 0 starts PPD_PAD_ROWS rows in
+  const Track trk{r->map->dev_table + (size_t)PPD_PAD_ROWS * PP_MAP_STRIDE, r->map->n, PP_MAP_STRIDE};
+  const int grid = (int)((r->n + kB - 1) / kB);
+  for (int64_t t = 0; t < n_ticks; t++) {
+    k_sim_frames<<<grid, kB, 0, st>>>(trk, r->n, r->c, r->ego_x, r->ego_y, r->ego_yaw, r->ego_mph,
+                                      r->path_n, r->path_x, r->path_y, r->target_lane, r->car_lane,
+                                      r->car_wp, r->car_ratio, r->car_speed, r->fr);
+    int rc = pp_plan_batch(r->map, cfg, &r->fr, &r->pl, r->n, st);
+    if (rc != PP_OK) return rc;
+    rc = pp_stats_batch(&r->pl, r->n, r->stats_tick, st);
+    if (rc != PP_OK) return rc;
+    k_add_stats<<<1, 64, 0, st>>>(r->stats_sum, r->stats_tick);
+    k_sim_advance<<<grid, kB, 0, st>>>(trk, r->n, r->c, r->seed, r->first, r->tick, consume_k,
+                                       r->ego_x, r->ego_y, r->ego_mph, r->path_n, r->path_x,
+                                       r->path_y, r->target_lane, r->car_lane, r->car_wp,
+                                       r->car_ratio, r->car_speed, r->pl);
+    ppi::count_launch(3);
+    r->tick++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail("rollout tick", e);
+  }
+  return PP_OK;
+}
+
+extern "C" int pp_rollouts_last(const pp_rollouts *r, pp_frames *frames_dev, pp_plans *plans_dev) {
+  if (!r) return PP_E_ARG;
+  if (frames_dev) *frames_dev = r->fr;
+  if (plans_dev) *plans_dev = r->pl;
+  return PP_OK;
+}
+
+extern "C" int pp_rollouts_get_state(const pp_rollouts *r, pp_rollout_state *h) {
+  if (!r || !h) return PP_E_ARG;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return cuda_fail("pp_rollouts_get_state", e);
+  const size_t N = (size_t)r->n, NC = (size_t)r->n * (size_t)r->c;
+  bool ok = true;
+  auto dn = [&](void *dst, const void *src, size_t bytes) {
+    if (dst && bytes && cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
+  };
+  dn(h->ego_x, r->ego_x, N * 8);
+  dn(h->ego_y, r->ego_y, N * 8);
+  dn(h->ego_yaw_deg, r->ego_yaw, N * 8);
+  dn(h->ego_speed_mph, r->ego_mph, N * 8);
+  dn(h->path_n, r->path_n, N * 4);
+  dn(h->path_x, r->path_x, N * PP_PATH_LEN * 8);
+  dn(h->path_y, r->path_y, N * PP_PATH_LEN * 8);
+  dn(h->target_lane, r->target_lane, N * 4);
+  dn(h->car_lane, r->car_lane, NC * 4);
+  dn(h->car_wp, r->car_wp, NC * 4);
+  dn(h->car_ratio, r->car_ratio, NC * 8);
+  dn(h->car_speed, r->car_speed, NC * 8);
+  h->tick = r->tick;
+  if (!ok) return cuda_fail("pp_rollouts_get_state copy", cudaGetLastError());
+  return PP_OK;
+}
+
+extern "C" int pp_rollouts_stats(const pp_rollouts *r, int64_t *stats_dev, void *cuda_stream) {
+  if (!r || !stats_dev) return PP_E_ARG;
+  cudaError_t e = cudaMemcpyAsync(stats_dev, r->stats_sum, PP_STATS_LEN * sizeof(int64_t),
+                                  cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail("pp_rollouts_stats", e);
+  return PP_OK;
+}

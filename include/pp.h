@@ -341,6 +341,57 @@ int pp_selftest_math(int64_t n, uint64_t seed, int64_t *counts_dev, void *cuda_s
 int pp_synth_frames(const pp_map *map, uint64_t seed, int64_t first_frame, int64_t n_frames,
                     int32_t n_cars, int32_t rare_permille, const pp_frames *out);
 
+/* ---- closed-loop rollouts (BASELINE config 3) -----------------
+ * R independent ego vehicles, each driving in closed loop against its own
+ * planner output and its own synthetic traffic, entirely on the device:
+ *
+ *   every tick   frame  <- simulator state        (kernel)
+ *                plan   <- pp_plan_batch(frame)    (the pipeline above)
+ *                state  <- simulator step(plan)    (kernel)
+ *
+ * The simulator model stands in for the Udacity term-3 simulator the reference
+ * was validated against (README.md:12-17); it is defined here, not in the
+ * reference, and restated on the CPU in oracle/ for the parity tests:
+ *   - the ego is moved to the consume_k-th point of the returned trajectory, the
+ *     remaining points become previous_path (src/main.cpp:1248-1249), target_lane
+ *     is carried over (:1195);  speed_mph = distance moved / (0.02 k) * 2.237;
+ *     yaw stays at its initial value (the planner only reads it on a cold start);
+ *   - each car keeps (lane, segment, ratio, speed) and advances along its lane
+ *     centre line at constant speed; x, y, vx, vy are derived from that;
+ *   - a car whose ego-centred s (as matched by the planner this tick) leaves
+ *     [-100, 300] m, or that the planner dropped, is respawned ahead (200-300 m)
+ *     if it fell behind, behind (60-100 m) otherwise, in a random lane at
+ *     50 +- 10 mph, from a counter-based generator keyed by (seed, rollout, car, tick).
+ * All of it is + - * / only, so the CPU restatement is bit-identical. */
+typedef struct pp_rollouts pp_rollouts; /* opaque: owns the device state */
+
+/* Host view of the simulator state (caller-owned arrays, R rollouts, C cars). */
+typedef struct pp_rollout_state {
+  double *ego_x, *ego_y, *ego_yaw_deg, *ego_speed_mph; /* [R] */
+  int32_t *path_n;                                     /* [R] unconsumed points of the last plan */
+  double *path_x, *path_y;                             /* [R][50] */
+  int32_t *target_lane;                                /* [R] */
+  int32_t *car_lane, *car_wp;                          /* [R][C] lane, segment end waypoint (0..n-1) */
+  double *car_ratio, *car_speed;                       /* [R][C] position along the segment, m/s */
+  int64_t tick;                                        /* ticks simulated so far */
+} pp_rollout_state;
+
+/* Initial state r = a pure function of (seed, first_rollout + r): ego at rest on a random lane
+ * centre (cold start), n_cars cars within [-100, 300] m.  Built on the host, uploaded. */
+int pp_rollouts_create(const pp_map *map, int64_t n_rollouts, int32_t n_cars, uint64_t seed,
+                       int64_t first_rollout, pp_rollouts **out);
+void pp_rollouts_destroy(pp_rollouts *r);
+/* n_ticks closed-loop ticks, consume_k (1..40) points per tick; asynchronous on cuda_stream. */
+int pp_rollouts_run(pp_rollouts *r, const pp_config *cfg, int64_t n_ticks, int32_t consume_k,
+                    void *cuda_stream);
+/* Device views of the LAST tick's frames and plans (valid until the next run / destroy). */
+int pp_rollouts_last(const pp_rollouts *r, pp_frames *frames_dev, pp_plans *plans_dev);
+/* Copy the simulator state out (synchronises the device). */
+int pp_rollouts_get_state(const pp_rollouts *r, pp_rollout_state *host_out);
+/* Sum over all ticks so far of the per-tick pp_stats_batch vectors: stats_dev[PP_STATS_LEN]
+ * (device, int64).  The multi-GPU job all-reduces this. */
+int pp_rollouts_stats(const pp_rollouts *r, int64_t *stats_dev, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1249,3 +1249,139 @@ void ppo_trajectory_build(ppo_map *m, const int32_t *prev_n, const double *prev_
     out_flags[i] = fl;
   }
 }
+
+/* ==========================================================================
+ * Simulator model of the closed-loop rollouts (BASELINE config 3).  NOT part of
+ * the reference (the reference was validated against the Udacity simulator
+ * binary, README.md:12-17): the model is specified in include/pp.h
+ * (pp_rollouts) and restated here independently of the CUDA code so that the
+ * tests can check the device state tick by tick, bit for bit.  Only + - * /
+ * and sqrt are used.
+ * ========================================================================== */
+static uint64_t sim_mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static double sim_u01(uint64_t v) { return (double)(v >> 11) * (1.0 / 9007199254740992.0); }
+
+static void sim_walk(const ppo_map *m, int *w, double *u, int lane, double ds) {
+  for (int guard = 0; guard < 4 * m->n; guard++) {
+    const double l = lane_length(m, *w, lane);
+    if (ds >= 0) {
+      const double rem = l * (1 - *u);
+      if (ds <= rem) {
+        *u += ds / l;
+        break;
+      }
+      ds -= rem;
+      *u = 0;
+      (*w)++;
+    } else {
+      const double rem = l * *u;
+      if (-ds <= rem) {
+        *u += ds / l;
+        break;
+      }
+      ds += rem;
+      *u = 1;
+      (*w)--;
+    }
+  }
+  *w %= m->n;
+  if (*w < 0) *w += m->n;
+}
+
+/* frame <- state */
+void ppo_sim_frames(ppo_map *m, const pp_rollout_state *st, int64_t n, int32_t c,
+                    const pp_frames *fr) {
+  for (int64_t r = 0; r < n; r++) {
+    ((double *)fr->ego_x)[r] = st->ego_x[r];
+    ((double *)fr->ego_y)[r] = st->ego_y[r];
+    ((double *)fr->ego_yaw_deg)[r] = st->ego_yaw_deg[r];
+    ((double *)fr->ego_speed_mph)[r] = st->ego_speed_mph[r];
+    const int pn = st->path_n[r];
+    ((int32_t *)fr->prev_n)[r] = pn;
+    for (int i = 0; i < PP_PREV_KEEP; i++) {
+      ((double *)fr->prev_x)[r * PP_PREV_KEEP + i] = i < pn ? st->path_x[r * PP_PATH_LEN + i] : 0.0;
+      ((double *)fr->prev_y)[r * PP_PREV_KEEP + i] = i < pn ? st->path_y[r * PP_PATH_LEN + i] : 0.0;
+    }
+    ((int32_t *)fr->target_lane_in)[r] = st->target_lane[r];
+    ((int32_t *)fr->n_cars)[r] = c;
+    for (int j = 0; j < c; j++) {
+      const int64_t k = r * c + j;
+      const int lane = st->car_lane[k], w = st->car_wp[k];
+      const vec2 a = wp_center(m, w - 1, lane), b = wp_center(m, w, lane);
+      const double l = lane_length(m, w, lane);
+      const double u = st->car_ratio[k], v = st->car_speed[k];
+      const double tx = (b.x - a.x) / l, ty = (b.y - a.y) / l;
+      ((int32_t *)fr->car_id)[k] = j;
+      ((double *)fr->car_x)[k] = a.x + (b.x - a.x) * u;
+      ((double *)fr->car_y)[k] = a.y + (b.y - a.y) * u;
+      ((double *)fr->car_vx)[k] = v * tx;
+      ((double *)fr->car_vy)[k] = v * ty;
+    }
+  }
+}
+
+/* state <- simulator step(plan) */
+void ppo_sim_advance(ppo_map *m, pp_rollout_state *st, int64_t n, int32_t c, uint64_t seed,
+                     int64_t first, int32_t consume_k, const pp_plans *pl) {
+  const double tick_s = 0.02;
+  for (int64_t r = 0; r < n; r++) {
+    const int np = pl->n_points[r];
+    const int k = consume_k < np ? consume_k : np;
+    const double *nx = pl->next_x + r * PP_PATH_LEN, *ny = pl->next_y + r * PP_PATH_LEN;
+    if (k > 0) {
+      const double ox = st->ego_x[r], oy = st->ego_y[r];
+      const double qx = nx[k - 1], qy = ny[k - 1];
+      const double d = sqrt((qx - ox) * (qx - ox) + (qy - oy) * (qy - oy));
+      st->ego_x[r] = qx;
+      st->ego_y[r] = qy;
+      st->ego_speed_mph[r] = d / (tick_s * k) * 2.237;
+    }
+    for (int i = 0; i < PP_PATH_LEN; i++) {
+      st->path_x[r * PP_PATH_LEN + i] = i + k < np ? nx[i + k] : 0.0;
+      st->path_y[r * PP_PATH_LEN + i] = i + k < np ? ny[i + k] : 0.0;
+    }
+    st->path_n[r] = np - k;
+    st->target_lane[r] = pl->target_lane[r];
+    const double dt = tick_s * (k > 0 ? k : 1);
+    const int ref_wp = pl->ref_wp[r];
+    for (int j = 0; j < c; j++) {
+      const int64_t q = r * c + j;
+      int lane = st->car_lane[q], w = st->car_wp[q];
+      double u = st->car_ratio[q], v = st->car_speed[q];
+      const int m_lane = pl->car_lane[q];
+      const double m_s = pl->car_s[q];
+      if (m_lane < 0 || m_s < -100.0 || m_s > 300.0) {
+        const uint64_t key =
+            sim_mix64(sim_mix64(seed ^ 0x5157ull) ^ ((uint64_t)(first + r) * 0xD1B54A32D192ED03ull));
+        const uint64_t h =
+            sim_mix64(key ^ ((uint64_t)st->tick * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)j << 48));
+        const double u1 = sim_u01(sim_mix64(h + 1)), u2 = sim_u01(sim_mix64(h + 2)),
+                     u3 = sim_u01(sim_mix64(h + 3));
+        const double ds = (m_lane >= 0 && m_s < -100.0) ? 200.0 + 100.0 * u1 : -(60.0 + 40.0 * u1);
+        lane = (int)(3.0 * u2);
+        if (lane > 2) lane = 2;
+        v = 17.88 + 8.94 * u3;
+        w = ref_wp;
+        u = 0.5;
+        sim_walk(m, &w, &u, lane, ds);
+      } else {
+        u += (v * dt) / lane_length(m, w, lane);
+        for (int guard = 0; guard < 64 && u >= 1; guard++) {
+          const double left = (u - 1) * lane_length(m, w, lane);
+          w = w + 1 == m->n ? 0 : w + 1;
+          u = left / lane_length(m, w, lane);
+        }
+      }
+      st->car_lane[q] = lane;
+      st->car_wp[q] = w;
+      st->car_ratio[q] = u;
+      st->car_speed[q] = v;
+    }
+  }
+  st->tick++;
+}

@@ -228,6 +228,25 @@ class Checker:
                                      C.c_int64(n))
         return ox, oy, on, fl
 
+    # ---- simulator model of the closed-loop rollouts (oracle only) ----
+    def sim_frames(self, state, n_cars):
+        """frame <- state.  `state`: the package's RolloutStateHost."""
+        assert self.kind == "oracle"
+        fb = abi.FrameBatch(state.n, max(n_cars, 1))
+        st, fs = state.struct(), fb.struct()
+        self._fn("sim_frames")(self.map, C.byref(st), C.c_int64(state.n), C.c_int32(n_cars),
+                               C.byref(fs))
+        return fb
+
+    def sim_advance(self, state, n_cars, seed, first, consume_k, plans):
+        """state <- simulator step(plan), in place (tick incremented)."""
+        assert self.kind == "oracle"
+        st, ps = state.struct(), plans.struct()
+        self._fn("sim_advance")(self.map, C.byref(st), C.c_int64(state.n), C.c_int32(n_cars),
+                                C.c_uint64(seed), C.c_int64(first), C.c_int32(consume_k),
+                                C.byref(ps))
+        state.tick = int(st.tick)
+
     def lambda_sequence(self, frames):
         """ref only: the untouched onMessage lambda over a frame SEQUENCE."""
         assert self.kind == "ref"
