@@ -65,12 +65,12 @@ def cpu_checker():
     return checkers.Checker("oracle"), "port"
 
 
-def time_cpu(pp, m, n_frames, passes=1):
+def time_cpu(pp, m, n_frames, passes=1, cars=N_CARS):
     """Reference CPU implementation of the path on all host threads."""
     chk, kind = cpu_checker()
     threads = cpu_threads()
-    frames = pp.synth_frames(m, n_frames, N_CARS, seed=SEED)
-    plans = pp.PlanBatch(n_frames, N_CARS, diag=True, cars=False)
+    frames = pp.synth_frames(m, n_frames, cars, seed=SEED)
+    plans = pp.PlanBatch(n_frames, cars, diag=True, cars=False)
     best = float("inf")
     for _ in range(passes):
         t0 = time.perf_counter()
@@ -91,7 +91,7 @@ def run_reference(args):
     total_t, total_f = 0.0, 0
     kind, threads = None, None
     for i in range(args.warmup + args.steps):
-        fps, t, kind, threads = time_cpu(pp, m, n)
+        fps, t, kind, threads = time_cpu(pp, m, n, cars=args.cars)
         if i >= args.warmup:
             total_t += t
             total_f += n
@@ -128,7 +128,7 @@ def run_rollouts(args):
     pp = load_package()
     m = pp.Map()
     n, ticks = args.rollouts, args.ticks
-    ro = pp.Rollouts(m, n, N_CARS, seed=SEED, first=rank * n)
+    ro = pp.Rollouts(m, n, args.cars, seed=SEED, first=rank * n)
     ro.run(max(3, min(20, ticks)), args.consume_k)  # warm-up ticks (also leaves the cold start)
     torch.cuda.synchronize()
     if world > 1:
@@ -158,7 +158,7 @@ def run_rollouts(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": f"configs[2]: {n} closed-loop rollouts x {ticks} ticks per GPU, "
-                                       f"{N_CARS} cars, consume_k={args.consume_k}",
+                                       f"{args.cars} cars, consume_k={args.consume_k}",
                            "ms_per_tick": ms / steps / ticks},
                 "gpu_launches": int(pp.launch_count() - launches0), "clocks": clocks,
                 "stats": {"frames": int(stats[0]), "points": int(stats[1]),
@@ -239,6 +239,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--cars", type=int, default=N_CARS,
+                    help="cars per frame (12 = configs[1], the headline; 64 = configs[4])")
     ap.add_argument("--workload", default="frames", choices=["frames", "rollouts"],
                     help="frames = BASELINE configs[1] (the headline metric, default); "
                          "rollouts = configs[2], closed-loop rollouts (secondary line)")
@@ -269,9 +271,9 @@ def main():
 
     n = args.frames
     m = pp.Map()
-    frames = pp.synth_frames(m, n, N_CARS, seed=SEED, first_frame=rank * n)
+    frames = pp.synth_frames(m, n, args.cars, seed=SEED, first_frame=rank * n)
     df = pp.DeviceFrames(frames)
-    dp = pp.DevicePlans(n, N_CARS, diag=True, cars=False)
+    dp = pp.DevicePlans(n, args.cars, diag=True, cars=False)
     stream = torch.cuda.current_stream()
 
     def step():
@@ -323,12 +325,12 @@ def main():
     value = world * n * args.steps / (total_ms * 1e-3)
 
     # ---- end to end through the host entry point (pinned host buffers) ----
-    hf = pp.FrameBatch(n, N_CARS)
+    hf = pp.FrameBatch(n, args.cars)
     for k, v in frames.arrays().items():
         pinned = torch.from_numpy(v).pin_memory()
         setattr(hf, k, pinned.numpy())
         hf.__dict__.setdefault("_keep", []).append(pinned)
-    hp = pp.PlanBatch(n, N_CARS, diag=True, cars=False)
+    hp = pp.PlanBatch(n, args.cars, diag=True, cars=False)
     for k in hp.fields:
         pinned = torch.from_numpy(getattr(hp, k)).pin_memory()
         setattr(hp, k, pinned.numpy())
@@ -348,7 +350,8 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        alg_bytes = (BYTES_IN + BYTES_OUT) * n
+        bytes_in = 204 + 36 * args.cars
+        alg_bytes = (bytes_in + BYTES_OUT) * n
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
         # dram__bytes_read+write of the pipeline's kernels from the committed ncu capture
         # (profiles/traffic.json: bytes per 262,144-frame launch, summed over the kernels)
@@ -372,8 +375,10 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": n, "cars_per_frame": N_CARS,
-                       "l2_policy": "inputs+outputs (1.6 GB per step) are larger than the 126 MB L2",
+            "config": {"workload": WORKLOAD if args.cars == N_CARS and n == FRAMES_PER_GPU else
+                       f"{n} independent synthetic frames x {args.cars} cars x 3 lanes per GPU",
+                       "frames_per_gpu": n, "cars_per_frame": args.cars,
+                       "l2_policy": f"inputs+outputs ({(204 + 36 * args.cars + 884) * n / 1e9:.1f} GB per step) are larger than the 126 MB L2",
                        "kernel_variant": args.variant,
                        "step": "pp_plan_batch + pp_stats_batch" + (" + NCCL all-reduce(stats)" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": "frames/s",
@@ -387,7 +392,7 @@ def main():
                                    "4 chunks of 262,144 frames per step); dominant: "
                                    + max(kernels[:4], key=lambda k: k["ms_per_step"])["name"],
                          "kernel_ms": kern_ms, "kernels": kernels,
-                         "algorithmic_bytes_per_frame": BYTES_IN + BYTES_OUT,
+                         "algorithmic_bytes_per_frame": bytes_in + BYTES_OUT,
                          "algorithmic_bytes_per_step": alg_bytes,
                          "note": "FP64-issue / divergence bound, not HBM bound (DESIGN.md §2): "
                                  "1,520 B against ~35 k FP64-heavy instructions per frame"},
@@ -396,7 +401,7 @@ def main():
                       "lane_changes": int(stats[8])},
         }
         if not args.no_cpu and world == 1:
-            fps, secs, kind, threads = time_cpu(pp, m, n)
+            fps, secs, kind, threads = time_cpu(pp, m, n, cars=args.cars)
             line["cpu_baseline"] = {
                 "value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
                 "sample": f"all {n} frames of the workload, 1 pass, {threads} threads ({secs:.1f} s wall)"}
