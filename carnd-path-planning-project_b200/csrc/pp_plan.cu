@@ -578,11 +578,12 @@ k_decide(const double *__restrict__ map_table, int n_wp, const __grid_constant__
     reduce_cars(cfg, in, sc, f, c, tl_in, b, flags);
     const Decision d = stage_decide(cfg, in, out, f, c, b, tl_in, flags);
     flags = d.flags;
-    Spline sp;
+    KnotSweep sw;
+    sw.init();
     TrajFrame tf;
     traj_setup(m, cfg, c.rs, in.prev_x + f * PP_PREV_KEEP, in.prev_y + f * PP_PREV_KEEP, c.nprev,
                c.x, c.y, in.ego_yaw_deg[f], d.target_lane, c.d, c.vd, d.sc,
-               out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN, flags, sp, tf);
+               out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN, flags, sw, tf);
     double *e = sc.est + f;
     e[0 * sc.n] = d.sc.start;
     e[1 * sc.n] = d.sc.target;
@@ -603,15 +604,17 @@ k_decide(const double *__restrict__ map_table, int n_wp, const __grid_constant__
       sc.slow_qa[atomicAdd(sc.slow_na, 1)] = (int32_t)f;
       continue;
     }
-    spline_fit(sp);
-    const int r0 = tf.min_count > 0 ? tf.min_count - 1 : 0;
-    const int cnt = tf.nk - r0;
-    for (int k = 0; k < cnt; k++) {
-      e[(kEstHead + 0 * PPD_TAILK + k) * sc.n] = sp.x[r0 + k];
-      e[(kEstHead + 1 * PPD_TAILK + k) * sc.n] = sp.y[r0 + k];
-      e[(kEstHead + 2 * PPD_TAILK + k) * sc.n] = sp.a[r0 + k];
-      e[(kEstHead + 3 * PPD_TAILK + k) * sc.n] = sp.b[r0 + k];
-      e[(kEstHead + 4 * PPD_TAILK + k) * sc.n] = sp.c[r0 + k];
+    const int r0 = sw.r0;
+    const int cnt = sw.solve(tf.nk);  // a, b, c of the reachable rows (in up, dg, z)
+#pragma unroll
+    for (int k = 0; k < PPD_TAILK; k++) {
+      if (k < cnt) {
+        e[(kEstHead + 0 * PPD_TAILK + k) * sc.n] = sw.tx[k];
+        e[(kEstHead + 1 * PPD_TAILK + k) * sc.n] = sw.ty[k];
+        e[(kEstHead + 2 * PPD_TAILK + k) * sc.n] = sw.up[k];
+        e[(kEstHead + 3 * PPD_TAILK + k) * sc.n] = sw.dg[k];
+        e[(kEstHead + 4 * PPD_TAILK + k) * sc.n] = sw.z[k];
+      }
     }
     sc.e_nk[f] = cnt | (r0 > 0 ? kEstPartial : 0);
     sc.e_flags[f] = flags;
