@@ -566,8 +566,13 @@ __global__ void __launch_bounds__(kBlock, PP_PLAN_MINB)
 k_decide(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
          const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
          const __grid_constant__ Scratch sc, int64_t n) {
-  extern __shared__ __align__(16) double s_map[];
-  const MapView m = stage_map(s_map, map_table, n_wp);
+  // shared memory holds the spline sweep's rows (one column per thread); the map is only
+  // touched by the handful of get_lane_pos steps per frame and is read through L1 instead
+  extern __shared__ __align__(16) double s_rows[];  // [PPD_SWEEP_ROWS * PPD_TAILK][blockDim.x]
+  MapView m;
+  m.t = map_table + PPD_PAD * PP_MAP_STRIDE;
+  m.n = n_wp;
+  m.pad_lo = n_wp < PPD_PAD ? n_wp : PPD_PAD;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += stride) {
     FrameCtx c;
@@ -578,13 +583,13 @@ k_decide(const double *__restrict__ map_table, int n_wp, const __grid_constant__
     reduce_cars(cfg, in, sc, f, c, tl_in, b, flags);
     const Decision d = stage_decide(cfg, in, out, f, c, b, tl_in, flags);
     flags = d.flags;
+    double *e = sc.est + f;
     KnotSweep sw;
-    sw.init();
+    sw.init(s_rows + threadIdx.x, blockDim.x, e, sc.n, kEstHead);
     TrajFrame tf;
     traj_setup(m, cfg, c.rs, in.prev_x + f * PP_PREV_KEEP, in.prev_y + f * PP_PREV_KEEP, c.nprev,
                c.x, c.y, in.ego_yaw_deg[f], d.target_lane, c.d, c.vd, d.sc,
                out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN, flags, sw, tf);
-    double *e = sc.est + f;
     e[0 * sc.n] = d.sc.start;
     e[1 * sc.n] = d.sc.target;
     e[2 * sc.n] = d.sc.time;
@@ -605,17 +610,7 @@ k_decide(const double *__restrict__ map_table, int n_wp, const __grid_constant__
       continue;
     }
     const int r0 = sw.r0;
-    const int cnt = sw.solve(tf.nk);  // a, b, c of the reachable rows (in up, dg, z)
-#pragma unroll
-    for (int k = 0; k < PPD_TAILK; k++) {
-      if (k < cnt) {
-        e[(kEstHead + 0 * PPD_TAILK + k) * sc.n] = sw.tx[k];
-        e[(kEstHead + 1 * PPD_TAILK + k) * sc.n] = sw.ty[k];
-        e[(kEstHead + 2 * PPD_TAILK + k) * sc.n] = sw.up[k];
-        e[(kEstHead + 3 * PPD_TAILK + k) * sc.n] = sw.dg[k];
-        e[(kEstHead + 4 * PPD_TAILK + k) * sc.n] = sw.z[k];
-      }
-    }
+    const int cnt = sw.solve(tf.nk);  // a, b, c of the reachable rows -> emission state
     sc.e_nk[f] = cnt | (r0 > 0 ? kEstPartial : 0);
     sc.e_flags[f] = flags;
   }
@@ -1023,7 +1018,8 @@ extern "C" int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_f
   if ((rc = ensure_smem(plan_fused, smem)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_prep, smem)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_cars, smem)) != PP_OK) return rc;
-  if ((rc = ensure_smem(k_decide, smem)) != PP_OK) return rc;
+  const size_t smem_decide = (size_t)PPD_SWEEP_ROWS * PPD_TAILK * kBlock * sizeof(double);
+  if ((rc = ensure_smem(k_decide, smem_decide)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_slow, smem)) != PP_OK) return rc;
   const size_t smem_emit = (size_t)5 * PPD_TAILK * kBlock * sizeof(double);
   if ((rc = ensure_smem(k_emit, smem_emit)) != PP_OK) return rc;
@@ -1097,7 +1093,7 @@ extern "C" int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_f
       k_cars<<<grid_for((cnt * mc + kTileK - 1) / kTileK, 12), kBlock, smem, st>>>(map->dev_table, map->n, fin, fout, sc,
                                                            cnt);
     phase_mark(pe, 2, st);
-    k_decide<<<grid_for(cnt, 12), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, fin, fout, sc,
+    k_decide<<<grid_for(cnt, 12), kBlock, smem_decide, st>>>(map->dev_table, map->n, *cfg, fin, fout, sc,
                                                       cnt);
     phase_mark(pe, 3, st);
     // side stream: the frames k_decide queued, concurrently with k_emit and the next chunk
