@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -218,16 +219,29 @@ int pp_dev_sync(void) {
 // ---------------------------------------------------------------------------
 namespace {
 
-constexpr int kStreams = 3;
+#ifndef PP_HOST_STREAMS
+#define PP_HOST_STREAMS 3
+#endif
+constexpr int kStreams = PP_HOST_STREAMS;
 // Chunk schedule: small chunks at both ends (the first chunk's upload and the last chunk's
 // download are not overlapped with anything), large ones in the middle (a copy costs ~7 us
 // of set-up whatever its size, and every chunk is 37 copies).
-constexpr int64_t kChunkFirst = 16384;
-constexpr int64_t kChunkCap = 262144;
+constexpr int64_t kChunkFirst = 32768;  // gpurun_out/e2e_sweep.log: 22.3 ms per 1M frames
+constexpr int64_t kChunkCap = 131072;    // (the PCIe floor of the box is ~20 ms)
+
+// tuning knobs for experiments (profiles/): PP_HOST_CHUNK_FIRST / PP_HOST_CHUNK_CAP in frames
+int64_t env_i64(const char *name, int64_t dflt) {
+  const char *v = getenv(name);
+  if (!v || !*v) return dflt;
+  const long long k = atoll(v);
+  return k > 0 ? (int64_t)k : dflt;
+}
 
 std::vector<int64_t> chunk_schedule(int64_t n) {
+  static const int64_t first = env_i64("PP_HOST_CHUNK_FIRST", kChunkFirst);
+  static const int64_t cap = env_i64("PP_HOST_CHUNK_CAP", kChunkCap);
   std::vector<int64_t> head, tail;
-  int64_t rem = n, s = kChunkFirst;
+  int64_t rem = n, s = first < cap ? first : cap;
   while (rem > 0) {
     const int64_t h = s < rem ? s : rem;
     head.push_back(h);
@@ -236,7 +250,7 @@ std::vector<int64_t> chunk_schedule(int64_t n) {
     const int64_t t = s < rem ? s : rem;
     tail.push_back(t);
     rem -= t;
-    if (s < kChunkCap) s *= 2;
+    if (s < cap) s = s * 2 < cap ? s * 2 : cap;
   }
   head.insert(head.end(), tail.rbegin(), tail.rend());
   return head;
@@ -251,9 +265,9 @@ struct Staging {
   int device = -1;
   int max_cars = -1;
   int64_t cap = 0;
-  cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
-  char *in_buf[kStreams] = {nullptr, nullptr, nullptr};
-  char *out_buf[kStreams] = {nullptr, nullptr, nullptr};
+  cudaStream_t streams[kStreams] = {};
+  char *in_buf[kStreams] = {};
+  char *out_buf[kStreams] = {};
   size_t in_bytes = 0, out_bytes = 0;
   void release() {
     for (int i = 0; i < kStreams; i++) {
