@@ -27,6 +27,60 @@ int upload_map(pp_map *m);
 void free_map_device(pp_map *m);
 
 void set_cuda_error(const char *what, int cuda_err, const char *text);
+
+// pp_frames / pp_plans advanced by `lo` frames
+inline pp_frames offset_frames(const pp_frames &a, int64_t lo) {
+  pp_frames r = a;
+  const int64_t mc = a.max_cars;
+  r.ego_x += lo;
+  r.ego_y += lo;
+  r.ego_yaw_deg += lo;
+  r.ego_speed_mph += lo;
+  r.prev_n += lo;
+  r.prev_x += lo * PP_PREV_KEEP;
+  r.prev_y += lo * PP_PREV_KEEP;
+  r.target_lane_in += lo;
+  r.n_cars += lo;
+  if (r.car_id) r.car_id += lo * mc;
+  if (r.car_x) r.car_x += lo * mc;
+  if (r.car_y) r.car_y += lo * mc;
+  if (r.car_vx) r.car_vx += lo * mc;
+  if (r.car_vy) r.car_vy += lo * mc;
+  return r;
+}
+template <class T>
+inline void adv(T *&p, int64_t k) {
+  if (p) p += k;
+}
+inline pp_plans offset_plans(const pp_plans &a, int64_t lo, int64_t mc) {
+  pp_plans r = a;
+  adv(r.next_x, lo * PP_PATH_LEN);
+  adv(r.next_y, lo * PP_PATH_LEN);
+  adv(r.n_points, lo);
+  adv(r.ego_lane, lo);
+  adv(r.ref_wp, lo);
+  adv(r.target_lane, lo);
+  adv(r.flags, lo);
+  adv(r.ego_s, lo);
+  adv(r.ego_d, lo);
+  adv(r.ego_vs, lo);
+  adv(r.ego_vd, lo);
+  adv(r.ego_speed, lo);
+  adv(r.ego_acc, lo);
+  adv(r.target_speed, lo);
+  adv(r.target_time, lo);
+  adv(r.next_car_id, lo);
+  adv(r.next_car_in_target_lane, lo);
+  adv(r.car_s, lo * mc);
+  adv(r.car_d, lo * mc);
+  adv(r.car_vs, lo * mc);
+  adv(r.car_vd, lo * mc);
+  adv(r.car_lane, lo * mc);
+  adv(r.car_next_wp, lo * mc);
+  return r;
+}
+
+
 void count_launch(int n = 1);
 
 }  // namespace ppi

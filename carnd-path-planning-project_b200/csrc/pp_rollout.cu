@@ -6,6 +6,8 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "pp_internal.h"
@@ -24,7 +26,22 @@ struct pp_rollouts {
   // per-tick frames and plans
   pp_frames fr;
   pp_plans pl;
-  int64_t *stats_tick, *stats_sum;
+  int64_t *stats_tick, *stats_sum;  // stats_tick: one vector per group
+  // Rollouts are independent, so they are cut into kGroups ranges that tick on their own
+  // streams: one group's short kernels and side-stream tail overlap the other groups' work.
+  static constexpr int kGroups = 4;
+  cudaStream_t gs[kGroups] = {};
+  cudaEvent_t g_done[kGroups] = {};
+  cudaEvent_t fork = nullptr;
+  cudaStream_t origin = nullptr;  // graph capture / replay stream (the caller's may be the
+                                  // legacy default stream, which cannot be captured)
+  cudaEvent_t o_fork = nullptr, o_join = nullptr;
+  int64_t *tick_dev = nullptr;  // [kGroups] ticks done per group (device side of `tick`)
+  // one tick of every group, captured once and replayed (a tick is ~50 small launches)
+  cudaGraphExec_t graph = nullptr;
+  int32_t graph_k = 0;
+  pp_config graph_cfg;
+  int64_t launches_per_tick = 0;
 };
 
 namespace {
@@ -98,13 +115,13 @@ struct Track {
 
 // frame <- state (one thread per rollout)
 __global__ void __launch_bounds__(kB)
-k_sim_frames(Track trk, int64_t n, int c, const double *ego_x, const double *ego_y,
+k_sim_frames(Track trk, int64_t lo, int64_t n, int c, const double *ego_x, const double *ego_y,
              const double *ego_yaw, const double *ego_mph, const int32_t *path_n,
              const double *path_x, const double *path_y, const int32_t *target_lane,
              const int32_t *car_lane, const int32_t *car_wp, const double *car_ratio,
              const double *car_speed, pp_frames fr) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
+  const int64_t r = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= lo + n) return;
   const_cast<double *>(fr.ego_x)[r] = ego_x[r];
   const_cast<double *>(fr.ego_y)[r] = ego_y[r];
   const_cast<double *>(fr.ego_yaw_deg)[r] = ego_yaw[r];
@@ -132,12 +149,14 @@ k_sim_frames(Track trk, int64_t n, int c, const double *ego_x, const double *ego
 
 // state <- simulator step(plan) (one thread per rollout)
 __global__ void __launch_bounds__(kB)
-k_sim_advance(Track trk, int64_t n, int c, uint64_t seed, int64_t first, int64_t tick, int consume_k,
+k_sim_advance(Track trk, int64_t lo, int64_t n, int c, uint64_t seed, int64_t first,
+              const int64_t *__restrict__ tick_ptr, int consume_k,
               double *ego_x, double *ego_y, double *ego_mph, int32_t *path_n, double *path_x,
               double *path_y, int32_t *target_lane, int32_t *car_lane, int32_t *car_wp,
               double *car_ratio, double *car_speed, pp_plans pl) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
+  const int64_t r = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= lo + n) return;
+  const int64_t tick = *tick_ptr;
   // ---- the ego consumes k points of the new trajectory
   const int np = pl.n_points[r];
   const int k = consume_k < np ? consume_k : np;
@@ -192,9 +211,12 @@ k_sim_advance(Track trk, int64_t n, int c, uint64_t seed, int64_t first, int64_t
   }
 }
 
-__global__ void k_add_stats(int64_t *sum, const int64_t *tick) {
+// end of a group's tick: fold its statistics into the running sum, count the tick
+__global__ void k_end_tick(int64_t *sum, const int64_t *tick_stats, int64_t *tick_counter) {
   const int i = threadIdx.x;
-  if (i < PP_STATS_LEN) sum[i] += tick[i];
+  if (i < PP_STATS_LEN && tick_stats[i])
+    atomicAdd((unsigned long long *)&sum[i], (unsigned long long)tick_stats[i]);
+  if (i == 0) *tick_counter += 1;
 }
 
 inline size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -248,7 +270,8 @@ extern "C" int pp_rollouts_create(const pp_map *map, int64_t n, int32_t c, uint6
   const size_t p_i0 = take(N * 4), p_i1 = take(N * 4);
   const size_t p_cs = take(NC * 8), p_cd = take(NC * 8), p_cvs = take(NC * 8), p_cvd = take(NC * 8),
                p_cl = take(NC * 4), p_cw = take(NC * 4);
-  const size_t o_st = take(PP_STATS_LEN * 8), o_ss = take(PP_STATS_LEN * 8);
+  const size_t o_st = take(pp_rollouts::kGroups * PP_STATS_LEN * 8), o_ss = take(PP_STATS_LEN * 8);
+  const size_t o_tk = take(pp_rollouts::kGroups * 8);
   cudaError_t e = cudaMalloc((void **)&r->buf, off);
   if (e != cudaSuccess) {
     delete r;
@@ -311,6 +334,7 @@ extern "C" int pp_rollouts_create(const pp_map *map, int64_t n, int32_t c, uint6
   p.car_next_wp = (int32_t *)(b + p_cw);
   r->stats_tick = (int64_t *)(b + o_st);
   r->stats_sum = (int64_t *)(b + o_ss);
+  r->tick_dev = (int64_t *)(b + o_tk);
 
   // ---- initial state on the host: a pure function of (seed, first + r)
   std::vector<double> ex(N), ey(N), yaw(N), mph(N), cr(NC), cs(NC);
@@ -367,41 +391,149 @@ extern "C" int pp_rollouts_create(const pp_map *map, int64_t n, int32_t c, uint6
     delete r;
     return cuda_fail("cudaMemcpy(rollouts init)", e2);
   }
+  for (int g = 0; g < pp_rollouts::kGroups; g++) {
+    if (cudaStreamCreateWithFlags(&r->gs[g], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r->g_done[g], cudaEventDisableTiming) != cudaSuccess)
+      ok = false;
+  }
+  if (cudaEventCreateWithFlags(&r->fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&r->o_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&r->o_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&r->origin, cudaStreamNonBlocking) != cudaSuccess)
+    ok = false;
+  if (!ok) {
+    cudaError_t e2 = cudaGetLastError();
+    pp_rollouts_destroy(r);
+    return cuda_fail("rollout streams", e2);
+  }
   *out = r;
   return PP_OK;
 }
 
 extern "C" void pp_rollouts_destroy(pp_rollouts *r) {
   if (!r) return;
+  for (int g = 0; g < pp_rollouts::kGroups; g++) {
+    if (r->gs[g]) cudaStreamDestroy(r->gs[g]);
+    if (r->g_done[g]) cudaEventDestroy(r->g_done[g]);
+  }
+  if (r->fork) cudaEventDestroy(r->fork);
+  if (r->graph) cudaGraphExecDestroy(r->graph);
+  if (r->origin) cudaStreamDestroy(r->origin);
+  if (r->o_fork) cudaEventDestroy(r->o_fork);
+  if (r->o_join) cudaEventDestroy(r->o_join);
   if (r->buf) cudaFree(r->buf);
   delete r;
 }
+
+namespace {
+
+// One tick of every group: issued on the group streams, forked from / joined to `st`.
+int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStream_t st) {
+  // device rows of the padded table: logical row 0 starts PPD_PAD_ROWS rows in
+  const Track trk{r->map->dev_table + (size_t)PPD_PAD_ROWS * PP_MAP_STRIDE, r->map->n, PP_MAP_STRIDE};
+  // groups: contiguous ranges of rollouts (at least 4096 each, so that small jobs stay whole)
+  int groups = pp_rollouts::kGroups;
+  while (groups > 1 && r->n / groups < 4096) groups--;
+  const int64_t per = (r->n + groups - 1) / groups;
+  const int mc = r->fr.max_cars;
+  cudaEventRecord(r->fork, st);
+  for (int g = 0; g < groups; g++) cudaStreamWaitEvent(r->gs[g], r->fork, 0);
+  const int64_t launches0 = pp_launch_count();
+  for (int g = 0; g < groups; g++) {
+    const int64_t lo = g * per;
+    const int64_t cnt = (r->n - lo) < per ? (r->n - lo) : per;
+    if (cnt <= 0) continue;
+    cudaStream_t gs = r->gs[g];
+    const int grid = (int)((cnt + kB - 1) / kB);
+    const pp_frames fr = ppi::offset_frames(r->fr, lo);
+    const pp_plans pl = ppi::offset_plans(r->pl, lo, mc);
+    int64_t *stats_tick = r->stats_tick + (size_t)g * PP_STATS_LEN;
+    k_sim_frames<<<grid, kB, 0, gs>>>(trk, lo, cnt, r->c, r->ego_x, r->ego_y, r->ego_yaw, r->ego_mph,
+                                      r->path_n, r->path_x, r->path_y, r->target_lane, r->car_lane,
+                                      r->car_wp, r->car_ratio, r->car_speed, r->fr);
+    int rc = pp_plan_batch(r->map, cfg, &fr, &pl, cnt, gs);
+    if (rc != PP_OK) return rc;
+    rc = pp_stats_batch(&pl, cnt, stats_tick, gs);
+    if (rc != PP_OK) return rc;
+    k_sim_advance<<<grid, kB, 0, gs>>>(trk, lo, cnt, r->c, r->seed, r->first, r->tick_dev + g,
+                                       consume_k, r->ego_x, r->ego_y, r->ego_mph, r->path_n,
+                                       r->path_x, r->path_y, r->target_lane, r->car_lane, r->car_wp,
+                                       r->car_ratio, r->car_speed, r->pl);
+    k_end_tick<<<1, 64, 0, gs>>>(r->stats_sum, stats_tick, r->tick_dev + g);
+    ppi::count_launch(3);
+  }
+  r->launches_per_tick = pp_launch_count() - launches0;
+  for (int g = 0; g < groups; g++) {  // join
+    cudaEventRecord(r->g_done[g], r->gs[g]);
+    cudaStreamWaitEvent(st, r->g_done[g], 0);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("rollout tick", e);
+  return PP_OK;
+}
+
+bool same_cfg(const pp_config &a, const pp_config &b) { return std::memcmp(&a, &b, sizeof a) == 0; }
+
+}  // namespace
 
 extern "C" int pp_rollouts_run(pp_rollouts *r, const pp_config *cfg, int64_t n_ticks,
                                int32_t consume_k, void *cuda_stream) {
   if (!r || !cfg || n_ticks < 0 || consume_k < 1 || consume_k > PP_PATH_LEN - PP_PREV_KEEP)
     return PP_E_ARG;
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  // device rows of the padded table: logical row 0 starts PPD_PAD_ROWS rows in
-  const Track trk{r->map->dev_table + (size_t)PPD_PAD_ROWS * PP_MAP_STRIDE, r->map->n, PP_MAP_STRIDE};
-  const int grid = (int)((r->n + kB - 1) / kB);
+  if (n_ticks == 0) return PP_OK;
+  // A tick is ~50 short launches over 5 streams.  Replaying it as a captured CUDA graph is
+  // available (PP_ROLLOUT_GRAPH=1) but measured SLOWER than issuing it directly (83 M vs
+  // 132 M ego-frames/s on the same B200: the stream-ordered scratch allocations become graph
+  // memory nodes), so direct issue is the default; the host keeps well ahead of the device.
+  const bool use_graph = n_ticks >= 8 && getenv("PP_ROLLOUT_GRAPH") != nullptr;
+  if (use_graph) {
+    cudaStream_t caller = st;
+    cudaEventRecord(r->o_fork, caller);
+    st = r->origin;
+    cudaStreamWaitEvent(st, r->o_fork, 0);
+    if (r->graph && (r->graph_k != consume_k || !same_cfg(r->graph_cfg, *cfg))) {
+      cudaGraphExecDestroy(r->graph);
+      r->graph = nullptr;
+    }
+    if (!r->graph) {
+      // one direct tick first: sizes the stream-ordered pool and sets kernel attributes
+      int rc = issue_tick(r, cfg, consume_k, st);
+      if (rc != PP_OK) return rc;
+      r->tick++;
+      n_ticks--;
+      cudaGraph_t g = nullptr;
+      cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+      if (e != cudaSuccess) return cuda_fail("cudaStreamBeginCapture", e);
+      rc = issue_tick(r, cfg, consume_k, st);
+      e = cudaStreamEndCapture(st, &g);
+      if (rc != PP_OK || e != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        return rc != PP_OK ? rc : cuda_fail("cudaStreamEndCapture", e);
+      }
+      e = cudaGraphInstantiate(&r->graph, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) {
+        r->graph = nullptr;
+        return cuda_fail("cudaGraphInstantiate", e);
+      }
+      r->graph_k = consume_k;
+      r->graph_cfg = *cfg;
+    }
+    for (int64_t t = 0; t < n_ticks; t++) {
+      cudaError_t e = cudaGraphLaunch(r->graph, st);
+      if (e != cudaSuccess) return cuda_fail("cudaGraphLaunch", e);
+      ppi::count_launch((int)r->launches_per_tick);
+      r->tick++;
+    }
+    cudaEventRecord(r->o_join, st);
+    cudaStreamWaitEvent(caller, r->o_join, 0);
+    return PP_OK;
+  }
   for (int64_t t = 0; t < n_ticks; t++) {
-    k_sim_frames<<<grid, kB, 0, st>>>(trk, r->n, r->c, r->ego_x, r->ego_y, r->ego_yaw, r->ego_mph,
-                                      r->path_n, r->path_x, r->path_y, r->target_lane, r->car_lane,
-                                      r->car_wp, r->car_ratio, r->car_speed, r->fr);
-    int rc = pp_plan_batch(r->map, cfg, &r->fr, &r->pl, r->n, st);
+    const int rc = issue_tick(r, cfg, consume_k, st);
     if (rc != PP_OK) return rc;
-    rc = pp_stats_batch(&r->pl, r->n, r->stats_tick, st);
-    if (rc != PP_OK) return rc;
-    k_add_stats<<<1, 64, 0, st>>>(r->stats_sum, r->stats_tick);
-    k_sim_advance<<<grid, kB, 0, st>>>(trk, r->n, r->c, r->seed, r->first, r->tick, consume_k,
-                                       r->ego_x, r->ego_y, r->ego_mph, r->path_n, r->path_x,
-                                       r->path_y, r->target_lane, r->car_lane, r->car_wp,
-                                       r->car_ratio, r->car_speed, r->pl);
-    ppi::count_launch(3);
     r->tick++;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail("rollout tick", e);
   }
   return PP_OK;
 }

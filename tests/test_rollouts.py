@@ -10,6 +10,7 @@ divergence.
 CPU: the simulator model itself on the oracle planner (sanity of the model).
 """
 import copy
+import os
 
 import numpy as np
 import pytest
@@ -78,6 +79,42 @@ def test_rollout_ticks_match_cpu_model_and_planner(pp, oracle, consume_k):
     assert moved.min() > 0.5 and respawns > 0
     stats = ro.stats().cpu().numpy()
     assert stats[0] == n * ticks and stats[1] == 50 * n * ticks
+
+
+@pytest.mark.gpu
+def test_rollout_groups_and_graph_replay_match_cpu_model(pp, oracle):
+    """Enough rollouts for several stream groups, enough ticks for the captured-graph path:
+    the device state after T ticks equals tick-by-tick stepping of a second, identical job,
+    and the last tick is checked against the CPU planner and model."""
+    n, c, seed, ticks, k = 12288, 12, 21, 12, 2
+    m = pp.Map()
+    a = pp.Rollouts(m, n, c, seed=seed)
+    b = pp.Rollouts(m, n, c, seed=seed)
+    os.environ["PP_ROLLOUT_GRAPH"] = "1"
+    try:
+        a.run(ticks, k)        # >= 8 ticks: one direct tick, then graph replays
+    finally:
+        del os.environ["PP_ROLLOUT_GRAPH"]
+    for _ in range(ticks):
+        b.run(1, k)            # direct issue
+    sa, sb = a.state(), b.state()
+    for f in STATE_FIELDS:
+        assert np.array_equal(getattr(sa, f), getattr(sb, f)), f
+    assert sa.tick == sb.tick == ticks
+    assert np.array_equal(a.stats().cpu().numpy(), b.stats().cpu().numpy())
+    # one more tick, checked on the CPU
+    prev = sa
+    a.run(1, k)
+    frames, plans = a.last()
+    want_frames = oracle.sim_frames(prev, c)
+    for key, arr in frames.arrays().items():
+        assert np.array_equal(arr, getattr(want_frames, key)), key
+    assert_plans_match(plans, oracle.plan(frames, threads=8), "tick %d" % ticks)
+    cpu = cpu_state_from(pp, prev)
+    oracle.sim_advance(cpu, c, seed, 0, k, plans)
+    now = a.state()
+    for f in STATE_FIELDS:
+        assert np.array_equal(getattr(now, f), getattr(cpu, f)), f
 
 
 @pytest.mark.gpu
