@@ -28,6 +28,12 @@ void free_map_device(pp_map *m);
 
 void set_cuda_error(const char *what, int cuda_err, const char *text);
 
+// pp_plan.cu: the pipeline with caller-owned scratch (see there)
+size_t plan_scratch_bytes(int64_t n_frames, int max_cars);
+int plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_frames *in,
+                       const pp_plans *out, int64_t n_frames, void *cuda_stream,
+                       char *caller_scratch);
+
 // pp_frames / pp_plans advanced by `lo` frames
 inline pp_frames offset_frames(const pp_frames &a, int64_t lo) {
   pp_frames r = a;

@@ -945,8 +945,28 @@ extern "C" int pp_set_kernel_variant(int variant) {
   return PP_OK;
 }
 
+// Bytes of scratch the pipeline needs for a batch (0 for batches the fused kernel takes).
+size_t ppi::plan_scratch_bytes(int64_t n_frames, int max_cars) {
+  if (n_frames <= 0 || g_variant == 1 || (g_variant == 0 && n_frames < kFusedBelow)) return 0;
+  const int64_t chunk = n_frames < kPipeChunk ? n_frames : kPipeChunk;
+  const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
+  const int n_buf = n_chunks > 1 ? 2 : 1;
+  const size_t scratch = (scratch_bytes(chunk, max_cars) + 255) & ~(size_t)255;
+  return n_buf * scratch + (size_t)n_frames * 2 * sizeof(int32_t) +
+         (size_t)n_chunks * 2 * sizeof(int32_t) + 256;
+}
+
 extern "C" int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_frames *in,
                              const pp_plans *out, int64_t n_frames, void *cuda_stream) {
+  return ppi::plan_batch_scratch(map, cfg, in, out, n_frames, cuda_stream, nullptr);
+}
+
+// pp_plan_batch with the scratch supplied by the caller (plan_scratch_bytes; nullptr: taken
+// from the stream-ordered pool).  The rollout engine owns its scratch so that a tick is pure
+// kernel / memset / event work and can be replayed as a CUDA graph.
+int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_frames *in,
+                            const pp_plans *out, int64_t n_frames, void *cuda_stream,
+                            char *caller_scratch) {
   if (!map || !cfg || !in || !out || n_frames < 0) return PP_E_ARG;
   if (!map->dev_table) {
     ppi::set_cuda_error("pp_plan_batch: map has no device table (no usable CUDA device)", 0, "");
@@ -1009,12 +1029,14 @@ extern "C" int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_f
   const size_t scratch = (scratch_bytes(chunk, mc) + 255) & ~(size_t)255;
   const size_t queues = (size_t)n_frames * 2 * sizeof(int32_t);
   const size_t counters = (size_t)n_chunks * 2 * sizeof(int32_t);
-  char *buf = nullptr;
-  cudaError_t e = cudaMallocAsync((void **)&buf, n_buf * scratch + queues + counters + 256, st);
-  if (e != cudaSuccess) {
-    ppi::set_cuda_error("cudaMallocAsync(scratch)", (int)e, cudaGetErrorString(e));
-    cudaGetLastError();
-    return PP_E_CUDA;
+  char *buf = caller_scratch;
+  if (!buf) {
+    cudaError_t e = cudaMallocAsync((void **)&buf, n_buf * scratch + queues + counters + 256, st);
+    if (e != cudaSuccess) {
+      ppi::set_cuda_error("cudaMallocAsync(scratch)", (int)e, cudaGetErrorString(e));
+      cudaGetLastError();
+      return PP_E_CUDA;
+    }
   }
   Scratch scs[2] = {carve_scratch(buf, chunk, mc), carve_scratch(buf + (n_buf - 1) * scratch, chunk, mc)};
   int32_t *q_base = (int32_t *)(buf + n_buf * scratch);
@@ -1081,7 +1103,7 @@ extern "C" int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_f
                  "atan2 %d, fmod %d, sincos %d)\n",
                  (long long)n_frames, a, b, r[1], r[2], r[3], r[4]);
   }
-  cudaFreeAsync(buf, st);
+  if (!caller_scratch) cudaFreeAsync(buf, st);
   if (rc == PP_OK) rc = check_launch("plan pipeline join");
   return rc;
 }

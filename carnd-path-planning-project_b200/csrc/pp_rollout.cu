@@ -37,6 +37,7 @@ struct pp_rollouts {
                                   // legacy default stream, which cannot be captured)
   cudaEvent_t o_fork = nullptr, o_join = nullptr;
   int64_t *tick_dev = nullptr;  // [kGroups] ticks done per group (device side of `tick`)
+  char *scratch[kGroups] = {};  // the planning pipeline's scratch, one per group
   // one tick of every group, captured once and replayed (a tick is ~50 small launches)
   cudaGraphExec_t graph = nullptr;
   int32_t graph_k = 0;
@@ -413,6 +414,7 @@ extern "C" int pp_rollouts_create(const pp_map *map, int64_t n, int32_t c, uint6
 extern "C" void pp_rollouts_destroy(pp_rollouts *r) {
   if (!r) return;
   for (int g = 0; g < pp_rollouts::kGroups; g++) {
+    if (r->scratch[g]) cudaFree(r->scratch[g]);
     if (r->gs[g]) cudaStreamDestroy(r->gs[g]);
     if (r->g_done[g]) cudaEventDestroy(r->g_done[g]);
   }
@@ -451,7 +453,12 @@ int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStre
     k_sim_frames<<<grid, kB, 0, gs>>>(trk, lo, cnt, r->c, r->ego_x, r->ego_y, r->ego_yaw, r->ego_mph,
                                       r->path_n, r->path_x, r->path_y, r->target_lane, r->car_lane,
                                       r->car_wp, r->car_ratio, r->car_speed, r->fr);
-    int rc = pp_plan_batch(r->map, cfg, &fr, &pl, cnt, gs);
+    if (!r->scratch[g]) {
+      const size_t need = ppi::plan_scratch_bytes(per, mc);
+      if (need && cudaMalloc((void **)&r->scratch[g], need) != cudaSuccess)
+        return cuda_fail("cudaMalloc(rollout scratch)", cudaGetLastError());
+    }
+    int rc = ppi::plan_batch_scratch(r->map, cfg, &fr, &pl, cnt, gs, r->scratch[g]);
     if (rc != PP_OK) return rc;
     rc = pp_stats_batch(&pl, cnt, stats_tick, gs);
     if (rc != PP_OK) return rc;
@@ -482,11 +489,12 @@ extern "C" int pp_rollouts_run(pp_rollouts *r, const pp_config *cfg, int64_t n_t
     return PP_E_ARG;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   if (n_ticks == 0) return PP_OK;
-  // A tick is ~50 short launches over 5 streams.  Replaying it as a captured CUDA graph is
-  // available (PP_ROLLOUT_GRAPH=1) but measured SLOWER than issuing it directly (83 M vs
-  // 132 M ego-frames/s on the same B200: the stream-ordered scratch allocations become graph
-  // memory nodes), so direct issue is the default; the host keeps well ahead of the device.
-  const bool use_graph = n_ticks >= 8 && getenv("PP_ROLLOUT_GRAPH") != nullptr;
+  // A tick is ~50 short launches over 5 streams; issued directly the job is at the mercy of
+  // the host's launch rate (84-150 M ego-frames/s from box to box).  So one tick is captured
+  // and replayed as a CUDA graph (the pipeline's scratch is owned by the rollouts object, so
+  // the graph holds only kernels, memsets and event edges).  PP_ROLLOUT_NO_GRAPH=1 issues
+  // every tick directly.
+  const bool use_graph = n_ticks >= 8 && getenv("PP_ROLLOUT_NO_GRAPH") == nullptr;
   if (use_graph) {
     cudaStream_t caller = st;
     cudaEventRecord(r->o_fork, caller);
