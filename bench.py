@@ -169,6 +169,62 @@ def run_rollouts(args):
     return 0
 
 
+def run_sweep(args):
+    """BASELINE configs[3]: candidate sweep, 384 candidates per frame (compute bound).
+    One step = pp_sweep_batch over --frames frames (default 32,768); value = candidates/s."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from __graft_entry__ import load_package
+    pp = load_package()
+    m = pp.Map()
+    n = args.frames if args.frames != FRAMES_PER_GPU else 32768
+    frames = pp.synth_frames(m, n, args.cars, seed=SEED, first_frame=rank * n)
+    df = pp.DeviceFrames(frames)
+    steps = args.steps if args.steps != 50 else 5
+    for _ in range(max(3, args.warmup)):
+        out = pp.sweep_batch(m, df, want_scores=False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = pp.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        out = pp.sweep_batch(m, df, want_scores=False)
+    ev1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    if rank == 0:
+        cands = 384
+        best = out["best"].cpu().numpy()
+        line = {"metric": "sweep candidates/sec (384 candidate trajectories per frame)",
+                "value": world * n * cands * steps / (ms * 1e-3), "unit": "candidates/s",
+                "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"configs[3]: {n} frames x 384 candidates (3 lanes x 16 speeds x "
+                                       f"8 times) per GPU, {args.cars} cars",
+                           "frames_per_s": world * n * steps / (ms * 1e-3)},
+                "gpu_launches": int(pp.launch_count() - launches0), "clocks": clocks,
+                "stats": {"winning_lane_hist": [int((best // 128 == k).sum()) for k in range(3)]}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 class ClockSampler:
     """SM clock + throttle reasons sampled every ~5 ms through NVML on a thread while the
     timed region runs (nvidia-smi's own loop is too coarse for a sub-second region)."""
@@ -241,7 +297,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--cars", type=int, default=N_CARS,
                     help="cars per frame (12 = configs[1], the headline; 64 = configs[4])")
-    ap.add_argument("--workload", default="frames", choices=["frames", "rollouts"],
+    ap.add_argument("--workload", default="frames", choices=["frames", "rollouts", "sweep"],
                     help="frames = BASELINE configs[1] (the headline metric, default); "
                          "rollouts = configs[2], closed-loop rollouts (secondary line)")
     ap.add_argument("--rollouts", type=int, default=65536, help="rollouts per GPU")
@@ -252,6 +308,8 @@ def main():
         return run_reference(args)
     if args.workload == "rollouts":
         return run_rollouts(args)
+    if args.workload == "sweep":
+        return run_sweep(args)
     args.warmup = max(args.warmup, 3)
 
     import numpy as np

@@ -38,7 +38,7 @@ EXPORTS = [
     "pp_project_speed_batch",
     "pp_dev_alloc", "pp_dev_free", "pp_dev_upload", "pp_dev_download", "pp_dev_sync",
     "pp_rollouts_create", "pp_rollouts_destroy", "pp_rollouts_run", "pp_rollouts_last",
-    "pp_rollouts_get_state", "pp_rollouts_stats",
+    "pp_rollouts_get_state", "pp_rollouts_stats", "pp_sweep_batch",
 ]
 
 
@@ -316,3 +316,28 @@ class Rollouts:
             self.close()
         except Exception:
             pass
+
+
+def sweep_batch(m: Map, frames: DeviceFrames, cfg: Config | None = None, want_scores: bool = True,
+                stream=None):
+    """pp_sweep_batch (BASELINE config 4) on device-resident frames -> dict of torch tensors:
+    best [N] int32, best_score [N], next_x/next_y [N][50], n_points [N], scores [N][384]."""
+    import torch
+    cfg = cfg or default_config()
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    n = frames.n
+    out = {"best": torch.zeros(n, dtype=torch.int32, device="cuda"),
+           "best_score": torch.zeros(n, dtype=torch.float64, device="cuda"),
+           "next_x": torch.zeros((n, abi.PATH_LEN), dtype=torch.float64, device="cuda"),
+           "next_y": torch.zeros((n, abi.PATH_LEN), dtype=torch.float64, device="cuda"),
+           "n_points": torch.zeros(n, dtype=torch.int32, device="cuda"),
+           "scores": torch.zeros((n, abi.SWEEP_CANDS), dtype=torch.float64, device="cuda")
+           if want_scores else None}
+    so = abi.SweepOut()
+    for k, v in out.items():
+        setattr(so, k, v.data_ptr() if v is not None else None)
+    fs = frames.struct()
+    _check(lib.pp_sweep_batch(m.handle, C.byref(cfg), C.byref(fs), C.byref(so), C.c_int64(n),
+                              C.c_void_p(stream)), "pp_sweep_batch")
+    return out

@@ -111,6 +111,15 @@ class Plans(C.Structure):
     _fields_ = [(n, _dp) for n, _, _ in PLAN_FIELDS]
 
 
+SWEEP_LANES, SWEEP_SPEEDS, SWEEP_TIMES = 3, 16, 8
+SWEEP_CANDS = SWEEP_LANES * SWEEP_SPEEDS * SWEEP_TIMES
+SWEEP_BAD = 1e9
+
+
+class SweepOut(C.Structure):
+    _fields_ = [(n, _dp) for n in ("best", "best_score", "next_x", "next_y", "n_points", "scores")]
+
+
 ROLLOUT_STATE_FIELDS = [  # (name, dtype, inner) ; inner: 0 scalar, 'path', 'cars'
     ("ego_x", np.float64, 0), ("ego_y", np.float64, 0), ("ego_yaw_deg", np.float64, 0),
     ("ego_speed_mph", np.float64, 0), ("path_n", np.int32, 0), ("path_x", np.float64, "path"),

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpp_b200.so")
-SOURCES = ["pp_api.cu", "pp_plan.cu", "pp_units.cu", "pp_rollout.cu", "pp_map_host.cpp",
+SOURCES = ["pp_api.cu", "pp_plan.cu", "pp_units.cu", "pp_rollout.cu", "pp_sweep.cu", "pp_map_host.cpp",
            "pp_synth.cpp"]
 HEADERS = ["pp_device.cuh", "pp_internal.h", os.path.join("..", "..", "include", "pp.h")]
 

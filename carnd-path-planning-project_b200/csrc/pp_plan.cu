@@ -657,9 +657,8 @@ k_emit(const __grid_constant__ pp_config cfg, const __grid_constant__ pp_plans o
     kn.part = (code & kEstPartial) != 0;
     uint32_t flags = sc.e_flags[f];
     int bail;
-    const int np = traj_emit<true>(kn, cfg, ctl, cx, cy, ca, sa, sc.e_np[f],
-                                   out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN,
-                                   flags, bail);
+    ArrayOut pts{out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN};
+    const int np = traj_emit<true>(kn, cfg, ctl, cx, cy, ca, sa, sc.e_np[f], pts, flags, bail);
     if (bail) {
       sc.slow_qb[atomicAdd(sc.slow_nb, 1)] = (int32_t)f;
       if (sc.dbg) atomicAdd(sc.dbg + bail, 1);

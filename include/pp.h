@@ -341,6 +341,42 @@ int pp_selftest_math(int64_t n, uint64_t seed, int64_t *counts_dev, void *cuda_s
 int pp_synth_frames(const pp_map *map, uint64_t seed, int64_t first_frame, int64_t n_frames,
                     int32_t n_cars, int32_t rare_permille, const pp_frames *out);
 
+/* ---- candidate sweep (BASELINE config 4) --------------------------
+ * The reference plans ONE trajectory per frame and notes that "multiple
+ * trajectories could be calculated and checked" (README.md:207-208).  The sweep
+ * does that: for every frame, PP_SWEEP_CANDS = 3 target lanes x 16 target speeds
+ * x 8 target times, each candidate being
+ *     SpeedController sc(ego_speed); sc.add_limit_breakpoint(v_i, t_j);
+ *     TrajectoryBuilder().build(prev, ..., target_lane = lane, ..., sc)
+ * (src/main.cpp:493-533,565-1049) with v_i = i * max_speed / 15, t_j = 0.5 (j + 1) s,
+ * candidate index = (lane * 16 + i) * 8 + j.  A candidate is scored on its OUTPUT
+ * points P_0..P_{n-1} only (so that the reference's unmodified classes are the
+ * oracle), with V_k = (P_{k+1} - P_k) * 50 and A_k = (V_{k+1} - V_k) * 50:
+ *     score = |lane - target_lane|                        (target_lane: the planner's own
+ *                                                          decision for this frame, :1355-1369)
+ *           + (max_speed - mean_k |V_k|) / max_speed
+ *           + 0.5 * max(0, max_k |A_k| - maximum_acc)
+ * and PP_SWEEP_BAD (1e9) if the builder fell back to the angle-based generator
+ * (:848), produced fewer than 3 points, or the score is not a finite number
+ * below that (NaN points of a standstill candidate).  The lowest score wins (lowest index on
+ * ties) and its trajectory is returned. */
+#define PP_SWEEP_LANES 3
+#define PP_SWEEP_SPEEDS 16
+#define PP_SWEEP_TIMES 8
+#define PP_SWEEP_CANDS (PP_SWEEP_LANES * PP_SWEEP_SPEEDS * PP_SWEEP_TIMES)
+#define PP_SWEEP_BAD 1e9
+typedef struct pp_sweep_out {
+  int32_t *best;        /* [N] winning candidate index */
+  double *best_score;   /* [N] */
+  double *next_x;       /* [N][50] its trajectory (NaN beyond n_points) */
+  double *next_y;
+  int32_t *n_points;    /* [N] */
+  double *scores;       /* [N][PP_SWEEP_CANDS], may be NULL */
+} pp_sweep_out;
+/* in / out hold DEVICE pointers; asynchronous on cuda_stream. */
+int pp_sweep_batch(const pp_map *map, const pp_config *cfg, const pp_frames *in,
+                   const pp_sweep_out *out, int64_t n_frames, void *cuda_stream);
+
 /* ---- closed-loop rollouts (BASELINE config 3) -----------------
  * R independent ego vehicles, each driving in closed loop against its own
  * planner output and its own synthetic traffic, entirely on the device:
