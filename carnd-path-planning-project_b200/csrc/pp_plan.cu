@@ -616,13 +616,25 @@ k_decide(const double *__restrict__ map_table, int n_wp, const __grid_constant__
   }
 }
 
+template <class S>
+PPD_INLINE S make_sink(double *x, double *y);
+template <>
+PPD_INLINE ArrayOut make_sink<ArrayOut>(double *x, double *y) {
+  return ArrayOut{x, y};
+}
+template <>
+PPD_INLINE PairOut make_sink<PairOut>(double *x, double *y) {
+  return PairOut{x, y, 0.0, 0.0, -1};
+}
+
 // The emission loop (one thread per frame): no map, no spline fit, no library
 // transcendental — small code, few registers, many resident warps.  The
 // reachable knots are staged in shared memory (one column per thread).  A frame
 // that leaves the ranges the fast forms cover re-plans through k_slow.
 #ifndef PP_EMIT_MINB
-#define PP_EMIT_MINB 1
+#define PP_EMIT_MINB 4
 #endif
+template <class PointSink>  // PairOut when next_x / next_y are 16-byte aligned, else ArrayOut
 __global__ void __launch_bounds__(kBlock, PP_EMIT_MINB)
 k_emit(const __grid_constant__ pp_config cfg, const __grid_constant__ pp_plans out,
        const __grid_constant__ Scratch sc, int64_t n) {
@@ -657,7 +669,7 @@ k_emit(const __grid_constant__ pp_config cfg, const __grid_constant__ pp_plans o
     kn.part = (code & kEstPartial) != 0;
     uint32_t flags = sc.e_flags[f];
     int bail;
-    ArrayOut pts{out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN};
+    PointSink pts = make_sink<PointSink>(out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN);
     const int np = traj_emit<true>(kn, cfg, ctl, cx, cy, ca, sa, sc.e_np[f], pts, flags, bail);
     if (bail) {
       sc.slow_qb[atomicAdd(sc.slow_nb, 1)] = (int32_t)f;
@@ -992,7 +1004,9 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
   if ((rc = ensure_smem(k_decide, smem_decide)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_slow, smem)) != PP_OK) return rc;
   const size_t smem_emit = (size_t)5 * PPD_TAILK * kBlock * sizeof(double);
-  if ((rc = ensure_smem(k_emit, smem_emit)) != PP_OK) return rc;
+  if ((rc = ensure_smem(k_emit<ArrayOut>, smem_emit)) != PP_OK) return rc;
+  if ((rc = ensure_smem(k_emit<PairOut>, smem_emit)) != PP_OK) return rc;
+  const bool paired = (((uintptr_t)out->next_x | (uintptr_t)out->next_y) & 15) == 0;
 
   const bool fused = g_variant == 1 || (g_variant == 0 && n_frames < kFusedBelow);
   if (fused) {
@@ -1072,7 +1086,10 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     cudaEventRecord(side.ev_a, st);
     cudaStreamWaitEvent(side.st, side.ev_a, 0);
     k_fallback<<<side_grid, kBlock, 0, side.st>>>(fout, sc, sc.slow_qa, sc.slow_na);
-    k_emit<<<grid_for(cnt, 12), kBlock, smem_emit, st>>>(*cfg, fout, sc, cnt);
+    if (paired)  // (a row is 400 bytes: every frame of an aligned array is aligned)
+      k_emit<PairOut><<<grid_for(cnt, 12), kBlock, smem_emit, st>>>(*cfg, fout, sc, cnt);
+    else
+      k_emit<ArrayOut><<<grid_for(cnt, 12), kBlock, smem_emit, st>>>(*cfg, fout, sc, cnt);
     phase_mark(pe, 4, st);
     cudaEventRecord(side.ev_b, st);
     cudaStreamWaitEvent(side.st, side.ev_b, 0);

@@ -114,6 +114,7 @@ struct ScoreOut {
     py = y;
     n++;
   }
+  PPD_INLINE void flush() {}
   PPD_INLINE double score(const pp_config &cfg, int lane, int target_lane) const {
     if (n < 3) return PP_SWEEP_BAD;
     const double mean = vsum / (n - 1);
