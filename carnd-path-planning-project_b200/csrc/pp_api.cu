@@ -47,6 +47,7 @@ int upload_map(pp_map *m) {
     std::memcpy(&padded[(size_t)r * PP_MAP_STRIDE], &m->table[(size_t)src * PP_MAP_STRIDE],
                 PP_MAP_STRIDE * sizeof(double));
   }
+  padded.resize(padded.size() + 2, 0.0);  // slack: the kernels stage it in 16-byte granules
   const size_t bytes = padded.size() * sizeof(double);
   e = cudaMalloc(&m->dev_table, bytes);
   if (e != cudaSuccess) {

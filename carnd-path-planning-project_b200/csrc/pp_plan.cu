@@ -994,7 +994,7 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     return PP_E_ARG;
   if (n_frames == 0) return PP_OK;
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  const size_t smem = map_smem_doubles(map->n) * sizeof(double);
+  const size_t smem = map_stage_bytes(map->n);
   if (smem > 200 * 1024) return PP_E_RANGE;
   int rc;
   if ((rc = ensure_smem(plan_fused, smem)) != PP_OK) return rc;

@@ -286,7 +286,7 @@ int finish(const char *what) {
   return PP_OK;
 }
 inline int grid_for(int64_t n) { return (int)((n + kB - 1) / kB); }
-inline size_t map_smem(const pp_map *m) { return map_smem_doubles(m->n) * sizeof(double); }
+inline size_t map_smem(const pp_map *m) { return map_stage_bytes(m->n); }
 int need_map(const pp_map *m, const char *who) {
   if (!m) return PP_E_ARG;
   if (!m->dev_table) {
