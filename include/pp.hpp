@@ -593,8 +593,125 @@ class Planner {
   }
   Plan plan(const Frame &frame) { return plan(std::vector<Frame>(1, frame))[0]; }
 
+  // The candidate sweep (pp_sweep_batch): 3 lanes x 16 target speeds x 8 target times through
+  // SpeedController / TrajectoryBuilder, scored on the output points, best one returned.
+  struct Swept {
+    int best = -1;           // (lane * 16 + speed index) * 8 + time index
+    double score = 0;
+    std::vector<double> next_x, next_y;
+    std::vector<double> scores;  // all PP_SWEEP_CANDS
+    int lane() const { return best / (PP_SWEEP_SPEEDS * PP_SWEEP_TIMES); }
+  };
+  Swept sweep(const Frame &f) {
+    const size_t mc = f.sensor_fusion.empty() ? 1 : f.sensor_fusion.size();
+    if (mc > PP_MAX_CARS) throw Error(PP_E_RANGE, "Planner::sweep: more than PP_MAX_CARS cars");
+    double px[PP_PREV_KEEP] = {0}, py[PP_PREV_KEEP] = {0};
+    const int32_t pn = (int32_t)f.previous_path_x.size(), tl = f.target_lane,
+                  nc = (int32_t)f.sensor_fusion.size();
+    for (int k = 0; k < PP_PREV_KEEP && k < pn; k++) {
+      px[k] = f.previous_path_x[k];
+      py[k] = f.previous_path_y[k];
+    }
+    std::vector<int32_t> cid(mc, 0);
+    std::vector<double> cx(mc, 0.0), cy(mc, 0.0), cvx(mc, 0.0), cvy(mc, 0.0);
+    for (size_t j = 0; j < f.sensor_fusion.size(); j++) {
+      cid[j] = f.sensor_fusion[j].id;
+      cx[j] = f.sensor_fusion[j].x;
+      cy[j] = f.sensor_fusion[j].y;
+      cvx[j] = f.sensor_fusion[j].vx;
+      cvy[j] = f.sensor_fusion[j].vy;
+    }
+    using detail::Dev;
+    using detail::one;
+    Dev<double> ex = one(f.car_x), ey = one(f.car_y), eyaw = one(f.car_yaw), esp = one(f.car_speed),
+                dpx(px, PP_PREV_KEEP), dpy(py, PP_PREV_KEEP), dcx(cx), dcy(cy), dcvx(cvx), dcvy(cvy);
+    Dev<int32_t> dpn(&pn, 1), dtl(&tl, 1), dnc(&nc, 1), dcid(cid);
+    pp_frames in;
+    std::memset(&in, 0, sizeof in);
+    in.ego_x = ex.get();
+    in.ego_y = ey.get();
+    in.ego_yaw_deg = eyaw.get();
+    in.ego_speed_mph = esp.get();
+    in.prev_n = dpn.get();
+    in.prev_x = dpx.get();
+    in.prev_y = dpy.get();
+    in.target_lane_in = dtl.get();
+    in.n_cars = dnc.get();
+    in.car_id = dcid.get();
+    in.car_x = dcx.get();
+    in.car_y = dcy.get();
+    in.car_vx = dcvx.get();
+    in.car_vy = dcvy.get();
+    in.max_cars = (int32_t)mc;
+    Dev<int32_t> best(1), npts(1);
+    Dev<double> bs(1), nx(PP_PATH_LEN), ny(PP_PATH_LEN), sc(PP_SWEEP_CANDS);
+    pp_sweep_out out;
+    out.best = best.get();
+    out.best_score = bs.get();
+    out.next_x = nx.get();
+    out.next_y = ny.get();
+    out.n_points = npts.get();
+    out.scores = sc.get();
+    check(pp_sweep_batch(map_.handle(), &cfg_, &in, &out, 1, nullptr), "pp_sweep_batch");
+    check(pp_dev_sync(), "pp_dev_sync");
+    Swept r;
+    r.best = best.first();
+    r.score = bs.first();
+    const int n = npts.first();
+    const std::vector<double> x = nx.to_host(), y = ny.to_host();
+    r.next_x.assign(x.begin(), x.begin() + n);
+    r.next_y.assign(y.begin(), y.begin() + n);
+    r.scores = sc.to_host();
+    return r;
+  }
+
  private:
   const Map &map_;
+  pp_config cfg_;
+};
+
+// Closed-loop rollouts (pp_rollouts_*): n independent ego vehicles, each with its own synthetic
+// traffic, stepped on the device against their own plans.
+class Rollouts {
+ public:
+  Rollouts(const Map &map, int64_t n, int n_cars = 12, uint64_t seed = 0x5EED, int64_t first = 0)
+      : n_(n), cfg_(default_config()) {
+    check(pp_rollouts_create(map.handle(), n, n_cars, seed, first, &h_), "pp_rollouts_create");
+  }
+  ~Rollouts() { pp_rollouts_destroy(h_); }
+  Rollouts(const Rollouts &) = delete;
+  Rollouts &operator=(const Rollouts &) = delete;
+  void run(int64_t ticks, int consume_k = 1) {
+    check(pp_rollouts_run(h_, &cfg_, ticks, consume_k, nullptr), "pp_rollouts_run");
+    check(pp_dev_sync(), "pp_dev_sync");
+  }
+  struct Ego {
+    std::vector<double> x, y, speed_mph;
+    std::vector<int32_t> target_lane, path_n;
+    int64_t tick = 0;
+  };
+  Ego ego() const {
+    Ego e;
+    e.x.resize(n_);
+    e.y.resize(n_);
+    e.speed_mph.resize(n_);
+    e.target_lane.resize(n_);
+    e.path_n.resize(n_);
+    pp_rollout_state st;
+    std::memset(&st, 0, sizeof st);
+    st.ego_x = e.x.data();
+    st.ego_y = e.y.data();
+    st.ego_speed_mph = e.speed_mph.data();
+    st.target_lane = e.target_lane.data();
+    st.path_n = e.path_n.data();
+    check(pp_rollouts_get_state(h_, &st), "pp_rollouts_get_state");
+    e.tick = st.tick;
+    return e;
+  }
+
+ private:
+  pp_rollouts *h_ = nullptr;
+  int64_t n_;
   pp_config cfg_;
 };
 

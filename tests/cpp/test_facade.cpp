@@ -173,6 +173,25 @@ int main(int argc, char **argv) {
     for (int i = 0; i < 50; i++) EXPECT(qb.next_x[i] == pb[i].x && qb.next_y[i] == pb[i].y);
     EXPECT(close_rel(qb.ego_speed, 1.2999999999988825, 1e-9, 1e-9));
 
+    // candidate sweep on frame B: the winner is a real candidate with a full trajectory, and
+    // no candidate scores below it
+    pp::Planner::Swept sw = planner.sweep(b);
+    EXPECT(sw.best >= 0 && sw.best < PP_SWEEP_CANDS && sw.scores.size() == PP_SWEEP_CANDS);
+    EXPECT(sw.next_x.size() == 50 && sw.score < PP_SWEEP_BAD && sw.score == sw.scores[sw.best]);
+    for (double v : sw.scores) EXPECT(!(v < sw.score));
+    EXPECT(sw.next_x[9] == b.previous_path_x[9] && sw.lane() >= 0 && sw.lane() <= 2);
+
+    // closed-loop rollouts: 64 vehicles, 30 ticks — everybody moves, paths stay full
+    pp::Rollouts ro(map, 64, 12, 7);
+    const pp::Rollouts::Ego e0 = ro.ego();
+    ro.run(30, 2);
+    const pp::Rollouts::Ego e1 = ro.ego();
+    EXPECT(e1.tick == 30);
+    for (int i = 0; i < 64; i++) {
+      EXPECT(pp::distance(e0.x[i], e0.y[i], e1.x[i], e1.y[i]) > 0.05);
+      EXPECT(e1.path_n[i] == 48 && e1.target_lane[i] >= 0 && e1.target_lane[i] <= 2);
+    }
+
     // starter helpers: a round trip inside the documented domain
     std::vector<double> mx, my, ms;
     double s_acc = 0;
