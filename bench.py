@@ -4,6 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
+Secondary lines (not the headline): --workload rollouts (BASELINE configs[2], closed-loop
+ego-frames/s), --workload sweep (configs[3], candidate trajectories/s), --cars 64 (configs[4]).
+
 Default run: N=1, 50 timed steps after 3 warm-ups (a few seconds).
 
 One "step" = one pass of the hot path (pp_plan_batch, then the aggregate

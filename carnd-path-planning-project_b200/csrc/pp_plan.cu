@@ -55,8 +55,8 @@ constexpr int kBlock = 128;
 #ifndef PP_CARS_MINB
 #define PP_CARS_MINB 6
 #endif
-#ifndef PP_PLAN_MINB
-#define PP_PLAN_MINB 4
+#ifndef PP_DECIDE_MINB
+#define PP_DECIDE_MINB 4
 #endif
 
 // ---------------------------------------------------------------------------
@@ -562,7 +562,7 @@ PPD_INLINE void reduce_cars(const pp_config &cfg, const pp_frames &in, const Scr
 // Decision + trajectory set-up + spline fit (one thread per frame).  Frames whose
 // trajectory is the ordinary spline emission hand their state to k_emit; the
 // rest (angle-based generator, :848) go to the queue of k_slow.
-__global__ void __launch_bounds__(kBlock, PP_PLAN_MINB)
+__global__ void __launch_bounds__(kBlock, PP_DECIDE_MINB)
 k_decide(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
          const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
          const __grid_constant__ Scratch sc, int64_t n) {
