@@ -220,3 +220,27 @@ def test_closed_loop_teacher_forced(pp, torch_cuda, gmap, oracle, abi):
         nxt.car_y += nxt.car_vy * 0.02 * consumed
         cur = nxt
     assert changes > 0  # lane changes did happen somewhere in the rollout
+
+
+@pytest.mark.parametrize("kind,n_wp", [("circle", 40), ("ellipse", 400), ("circle", 7)])
+def test_other_maps(pp, torch_cuda, oracle, kind, n_wp):
+    """Tracks other than highway_map.csv: a small loop (every walk crosses the wrap-around seam,
+    the table is shorter than the staging pad), a long one (table past the default shared-memory
+    size), a degenerate 7-point loop (walks lap the whole table: the reference's unsigned index
+    arithmetic, src/main.cpp:134-137)."""
+    th = np.linspace(0.0, 2 * np.pi, n_wp, endpoint=False)
+    if kind == "circle":
+        r = 40.0 * n_wp / (2 * np.pi)           # ~40 m segments
+        wx, wy = 1000 + r * np.cos(-th), 2000 + r * np.sin(-th)   # clockwise, like the highway
+    else:
+        wx, wy = 3000 + 2400 * np.cos(-th), 1000 + 1100 * np.sin(-th)
+    chk = checkers.Checker("oracle")
+    chk.map_from_points(wx, wy)
+    m = pp.Map(points=(wx, wy))
+    assert np.array_equal(m.table(), chk.map_table())
+    for seed, cars, rare in ((1, 12, 100), (2, 64, 0)):
+        fb = pp.synth_frames(m, 2500, cars, seed=seed, rare_permille=rare, max_cars=cars)
+        want = chk.plan(fb, threads=8)
+        got = gpu_plan(pp, torch_cuda, m, fb)
+        assert_plans_equal(plans_dict(got), plans_dict(want), ALL_FLAGS, bitwise_traj=False,
+                           what=f"{kind}/{n_wp}/seed {seed}: ")
