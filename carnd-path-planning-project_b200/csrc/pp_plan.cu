@@ -765,27 +765,54 @@ stats_kernel(const __grid_constant__ pp_plans p, int64_t n, unsigned long long *
   // Four independent elements per trip and unconditional loads (the padding is valid memory,
   // n_points only masks it afterwards) keep enough requests in flight to reach HBM speed.
   long long xs = 0;
-  const int64_t total = n * PP_PATH_LEN;
+  const bool wide = (((uintptr_t)p.next_x | (uintptr_t)p.next_y) & 15) == 0;
   constexpr int kU = 4;
-  for (int64_t e0 = tid; e0 < total; e0 += stride * kU) {
-    double xv[kU], yv[kU];
-    int lim[kU], idx[kU];
+  auto add_point = [&](double x, double y, bool live) {
+    if (live && x == x && y == y && fabs(x) < 1e12 && fabs(y) < 1e12)
+      xs += (long long)(x * 256.0) + (long long)(y * 256.0);
+  };
+  if (wide) {  // two points per load: a row holds an even number of points
+    const int64_t total = n * (PP_PATH_LEN / 2);
+    const double2 *px = reinterpret_cast<const double2 *>(p.next_x);
+    const double2 *py = reinterpret_cast<const double2 *>(p.next_y);
+    for (int64_t e0 = tid; e0 < total; e0 += stride * kU) {
+      double2 xv[kU], yv[kU];
+      int lim[kU], idx[kU];
 #pragma unroll
-    for (int u = 0; u < kU; u++) {
-      const int64_t e = e0 + u * stride;
-      const bool in = e < total;
-      const int64_t ec = in ? e : 0;
-      const int64_t f = ec / PP_PATH_LEN;
-      idx[u] = (int)(ec - f * PP_PATH_LEN);
-      xv[u] = p.next_x[ec];
-      yv[u] = p.next_y[ec];
-      lim[u] = in ? p.n_points[f] : 0;
+      for (int u = 0; u < kU; u++) {
+        const int64_t e = e0 + u * stride;
+        const bool in = e < total;
+        const int64_t ec = in ? e : 0;
+        const int64_t f = ec / (PP_PATH_LEN / 2);
+        idx[u] = 2 * (int)(ec - f * (PP_PATH_LEN / 2));
+        xv[u] = px[ec];
+        yv[u] = py[ec];
+        lim[u] = in ? p.n_points[f] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        add_point(xv[u].x, yv[u].x, idx[u] < lim[u]);
+        add_point(xv[u].y, yv[u].y, idx[u] + 1 < lim[u]);
+      }
     }
+  } else {
+    const int64_t total = n * PP_PATH_LEN;
+    for (int64_t e0 = tid; e0 < total; e0 += stride * kU) {
+      double xv[kU], yv[kU];
+      int lim[kU], idx[kU];
 #pragma unroll
-    for (int u = 0; u < kU; u++) {
-      const double x = xv[u], y = yv[u];
-      if (idx[u] < lim[u] && x == x && y == y && fabs(x) < 1e12 && fabs(y) < 1e12)
-        xs += (long long)(x * 256.0) + (long long)(y * 256.0);
+      for (int u = 0; u < kU; u++) {
+        const int64_t e = e0 + u * stride;
+        const bool in = e < total;
+        const int64_t ec = in ? e : 0;
+        const int64_t f = ec / PP_PATH_LEN;
+        idx[u] = (int)(ec - f * PP_PATH_LEN);
+        xv[u] = p.next_x[ec];
+        yv[u] = p.next_y[ec];
+        lim[u] = in ? p.n_points[f] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < kU; u++) add_point(xv[u], yv[u], idx[u] < lim[u]);
     }
   }
   const unsigned long long xw = warp_sum((unsigned long long)xs);
