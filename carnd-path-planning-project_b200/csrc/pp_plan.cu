@@ -27,7 +27,7 @@
 // double-buffered, stream-ordered scratch in HBM.  The ncu evidence behind each
 // cut is in profiles/ (r1_v0: the single fused kernel, 45 % instruction-fetch
 // stalls on 155 KB of SASS at 15 of 32 lanes; r1b/r1c: the division of the
-// interior step at 4 lanes, the library atan2 at 3.6 lanes, knot staging; r1g:
+// interior step at 4 lanes, the library atan2 at 3.6 lanes, knot staging; r1h:
 // the current state).  The fused single-kernel form is kept as variant 1: it
 // has the lowest latency for small batches and is the bitwise cross-check of
 // the pipeline (tests/test_gpu_parity.py).
