@@ -47,6 +47,25 @@ WORKLOAD = "configs[1]: 1,048,576 independent synthetic frames x 12 cars x 3 lan
 METRIC = "planned frames/sec at 1M-frame batch"
 
 
+# Library chatter (e.g. "NCCL version ..." goes to fd 1) must not share stdout with the ONE JSON
+# line: fd 1 is pointed at stderr for the whole run and the line is written to the saved fd.
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -111,7 +130,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -166,7 +185,7 @@ def run_rollouts(args):
                 "gpu_launches": int(pp.launch_count() - launches0), "clocks": clocks,
                 "stats": {"frames": int(stats[0]), "points": int(stats[1]),
                           "lane_changes": int(stats[8])}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -222,7 +241,7 @@ def run_sweep(args):
                            "frames_per_s": world * n * steps / (ms * 1e-3)},
                 "gpu_launches": int(pp.launch_count() - launches0), "clocks": clocks,
                 "stats": {"winning_lane_hist": [int((best // 128 == k).sum()) for k in range(3)]}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -307,6 +326,7 @@ def main():
     ap.add_argument("--ticks", type=int, default=1000)
     ap.add_argument("--consume-k", type=int, default=1)
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "rollouts":
@@ -466,7 +486,7 @@ def main():
             line["cpu_baseline"] = {
                 "value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
                 "sample": f"all {n} frames of the workload, 1 pass, {threads} threads ({secs:.1f} s wall)"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
