@@ -901,7 +901,27 @@ struct Side {
   }
   // not destroyed at thread exit: the CUDA context may already be gone by then
 };
-thread_local Side t_side;
+// One side stream per caller stream (per host thread): callers that drive several streams at
+// once — the rollout engine's groups — must not serialise on each other's rare-frame kernels.
+constexpr int kMaxSides = 16;
+struct SideSlot {
+  cudaStream_t owner = nullptr;
+  bool used = false;
+  Side side;
+};
+thread_local SideSlot t_sides[kMaxSides];
+
+Side &side_for(cudaStream_t st) {
+  for (int i = 0; i < kMaxSides; i++)
+    if (t_sides[i].used && t_sides[i].owner == st) return t_sides[i].side;
+  for (int i = 0; i < kMaxSides; i++)
+    if (!t_sides[i].used) {
+      t_sides[i].used = true;
+      t_sides[i].owner = st;
+      return t_sides[i].side;
+    }
+  return t_sides[0].side;  // more caller streams than slots: share (still correct, ordered by events)
+}
 
 // ---- optional per-phase timing (bench.py / profiles): CUDA events recorded on
 // the caller's stream around every kernel of the pipeline.
@@ -1060,7 +1080,7 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
       pool_tuned[dev] = true;
     }
   }
-  Side &side = t_side;
+  Side &side = side_for(st);
   if ((rc = side.ensure()) != PP_OK) return rc;
   // Scratch is double buffered: the side stream may still be reading chunk i's while the
   // main stream fills chunk i+1's.

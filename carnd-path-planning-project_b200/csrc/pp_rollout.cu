@@ -26,7 +26,7 @@ struct pp_rollouts {
   // per-tick frames and plans
   pp_frames fr;
   pp_plans pl;
-  int64_t *stats_tick, *stats_sum;  // stats_tick: one vector per group
+  int64_t *stats_tick, *stats_sum;  // stats_sum: running sum over all ticks (stats_tick: spare)
   // Rollouts are independent, so they are cut into kGroups ranges that tick on their own
   // streams: one group's short kernels and side-stream tail overlap the other groups' work.
   static constexpr int kGroups = 4;
@@ -36,7 +36,7 @@ struct pp_rollouts {
   cudaStream_t origin = nullptr;  // graph capture / replay stream (the caller's may be the
                                   // legacy default stream, which cannot be captured)
   cudaEvent_t o_fork = nullptr, o_join = nullptr;
-  int64_t *tick_dev = nullptr;  // [kGroups] ticks done per group (device side of `tick`)
+  int64_t *tick_dev = nullptr;  // [R] ticks done per rollout (device side of `tick`)
   char *scratch[kGroups] = {};  // the planning pipeline's scratch, one per group
   // one tick of every group, captured once and replayed (a tick is ~50 small launches)
   cudaGraphExec_t graph = nullptr;
@@ -148,16 +148,59 @@ k_sim_frames(Track trk, int64_t lo, int64_t n, int c, const double *ego_x, const
   }
 }
 
-// state <- simulator step(plan) (one thread per rollout)
+__device__ __forceinline__ void sim_advance_one(
+    const Track &trk, int64_t r, int c, uint64_t seed, int64_t first, int64_t *__restrict__ ticks,
+    int consume_k, double *ego_x, double *ego_y, double *ego_mph, int32_t *path_n, double *path_x,
+    double *path_y, int32_t *target_lane, int32_t *car_lane, int32_t *car_wp, double *car_ratio,
+    double *car_speed, const pp_plans &pl);
+
+// state <- simulator step(plan) (one thread per rollout), and this tick's statistics
 __global__ void __launch_bounds__(kB)
 k_sim_advance(Track trk, int64_t lo, int64_t n, int c, uint64_t seed, int64_t first,
-              const int64_t *__restrict__ tick_ptr, int consume_k,
+              int64_t *__restrict__ ticks, int consume_k,
               double *ego_x, double *ego_y, double *ego_mph, int32_t *path_n, double *path_x,
               double *path_y, int32_t *target_lane, int32_t *car_lane, int32_t *car_wp,
-              double *car_ratio, double *car_speed, pp_plans pl) {
+              double *car_ratio, double *car_speed, pp_plans pl, unsigned long long *stats_sum) {
+  __shared__ unsigned long long s_acc[PP_STATS_LEN];
+  for (int i = threadIdx.x; i < PP_STATS_LEN; i += blockDim.x) s_acc[i] = 0;
+  __syncthreads();
   const int64_t r = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= lo + n) return;
-  const int64_t tick = *tick_ptr;
+  if (r < lo + n) {
+    // ---- this tick's contribution to the aggregate statistics (definition: pp_stats_batch)
+    {
+      const int np = pl.n_points[r];
+      const int tl = pl.target_lane[r], el = pl.ego_lane[r];
+      const uint32_t fl = pl.flags[r];
+      long long xs = 0;
+      for (int i = 0; i < np; i++) {
+        const double x = pl.next_x[r * PP_PATH_LEN + i], y = pl.next_y[r * PP_PATH_LEN + i];
+        if (x == x && y == y && fabs(x) < 1e12 && fabs(y) < 1e12)
+          xs += (long long)(x * 256.0) + (long long)(y * 256.0);
+      }
+      atomicAdd(&s_acc[PP_STAT_FRAMES], 1ull);
+      atomicAdd(&s_acc[PP_STAT_POINTS], (unsigned long long)np);
+      if (tl >= 0 && tl < 3) atomicAdd(&s_acc[PP_STAT_TARGET_LANE0 + tl], 1ull);
+      if (el >= 0 && el < 3) atomicAdd(&s_acc[PP_STAT_EGO_LANE0 + el], 1ull);
+      if (tl != el) atomicAdd(&s_acc[PP_STAT_LANE_CHANGES], 1ull);
+      for (int b = 0; b < PP_NUM_FLAGS; b++)
+        if (fl & (1u << b)) atomicAdd(&s_acc[PP_STAT_FLAG0 + b], 1ull);
+      if (xs) atomicAdd(&s_acc[PP_STAT_XSUM], (unsigned long long)xs);
+    }
+    sim_advance_one(trk, r, c, seed, first, ticks, consume_k, ego_x, ego_y, ego_mph, path_n, path_x,
+                    path_y, target_lane, car_lane, car_wp, car_ratio, car_speed, pl);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PP_STATS_LEN; i += blockDim.x)
+    if (s_acc[i]) atomicAdd(&stats_sum[i], s_acc[i]);
+}
+
+__device__ __forceinline__ void sim_advance_one(
+    const Track &trk, int64_t r, int c, uint64_t seed, int64_t first, int64_t *__restrict__ ticks,
+    int consume_k, double *ego_x, double *ego_y, double *ego_mph, int32_t *path_n, double *path_x,
+    double *path_y, int32_t *target_lane, int32_t *car_lane, int32_t *car_wp, double *car_ratio,
+    double *car_speed, const pp_plans &pl) {
+  const int64_t tick = ticks[r];  // every rollout counts its own ticks (all equal)
+  ticks[r] = tick + 1;
   // ---- the ego consumes k points of the new trajectory
   const int np = pl.n_points[r];
   const int k = consume_k < np ? consume_k : np;
@@ -212,14 +255,6 @@ k_sim_advance(Track trk, int64_t lo, int64_t n, int c, uint64_t seed, int64_t fi
   }
 }
 
-// end of a group's tick: fold its statistics into the running sum, count the tick
-__global__ void k_end_tick(int64_t *sum, const int64_t *tick_stats, int64_t *tick_counter) {
-  const int i = threadIdx.x;
-  if (i < PP_STATS_LEN && tick_stats[i])
-    atomicAdd((unsigned long long *)&sum[i], (unsigned long long)tick_stats[i]);
-  if (i == 0) *tick_counter += 1;
-}
-
 inline size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
 
 int cuda_fail(const char *what, cudaError_t e) {
@@ -272,7 +307,7 @@ extern "C" int pp_rollouts_create(const pp_map *map, int64_t n, int32_t c, uint6
   const size_t p_cs = take(NC * 8), p_cd = take(NC * 8), p_cvs = take(NC * 8), p_cvd = take(NC * 8),
                p_cl = take(NC * 4), p_cw = take(NC * 4);
   const size_t o_st = take(pp_rollouts::kGroups * PP_STATS_LEN * 8), o_ss = take(PP_STATS_LEN * 8);
-  const size_t o_tk = take(pp_rollouts::kGroups * 8);
+  const size_t o_tk = take(N * 8);
   cudaError_t e = cudaMalloc((void **)&r->buf, off);
   if (e != cudaSuccess) {
     delete r;
@@ -449,7 +484,6 @@ int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStre
     const int grid = (int)((cnt + kB - 1) / kB);
     const pp_frames fr = ppi::offset_frames(r->fr, lo);
     const pp_plans pl = ppi::offset_plans(r->pl, lo, mc);
-    int64_t *stats_tick = r->stats_tick + (size_t)g * PP_STATS_LEN;
     k_sim_frames<<<grid, kB, 0, gs>>>(trk, lo, cnt, r->c, r->ego_x, r->ego_y, r->ego_yaw, r->ego_mph,
                                       r->path_n, r->path_x, r->path_y, r->target_lane, r->car_lane,
                                       r->car_wp, r->car_ratio, r->car_speed, r->fr);
@@ -460,14 +494,12 @@ int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStre
     }
     int rc = ppi::plan_batch_scratch(r->map, cfg, &fr, &pl, cnt, gs, r->scratch[g]);
     if (rc != PP_OK) return rc;
-    rc = pp_stats_batch(&pl, cnt, stats_tick, gs);
-    if (rc != PP_OK) return rc;
-    k_sim_advance<<<grid, kB, 0, gs>>>(trk, lo, cnt, r->c, r->seed, r->first, r->tick_dev + g,
+    k_sim_advance<<<grid, kB, 0, gs>>>(trk, lo, cnt, r->c, r->seed, r->first, r->tick_dev,
                                        consume_k, r->ego_x, r->ego_y, r->ego_mph, r->path_n,
                                        r->path_x, r->path_y, r->target_lane, r->car_lane, r->car_wp,
-                                       r->car_ratio, r->car_speed, r->pl);
-    k_end_tick<<<1, 64, 0, gs>>>(r->stats_sum, stats_tick, r->tick_dev + g);
-    ppi::count_launch(3);
+                                       r->car_ratio, r->car_speed, r->pl,
+                                       (unsigned long long *)r->stats_sum);
+    ppi::count_launch(2);
   }
   r->launches_per_tick = pp_launch_count() - launches0;
   for (int g = 0; g < groups; g++) {  // join
@@ -489,12 +521,12 @@ extern "C" int pp_rollouts_run(pp_rollouts *r, const pp_config *cfg, int64_t n_t
     return PP_E_ARG;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   if (n_ticks == 0) return PP_OK;
-  // A tick is ~50 short launches over 5 streams; issued directly the job is at the mercy of
-  // the host's launch rate (84-150 M ego-frames/s from box to box).  So one tick is captured
-  // and replayed as a CUDA graph (the pipeline's scratch is owned by the rollouts object, so
-  // the graph holds only kernels, memsets and event edges).  PP_ROLLOUT_NO_GRAPH=1 issues
-  // every tick directly.
-  const bool use_graph = n_ticks >= 8 && getenv("PP_ROLLOUT_NO_GRAPH") == nullptr;
+  // A tick is ~50 short launches over 8 streams (4 groups, each with its side stream).  It can
+  // be captured once and replayed as a CUDA graph (PP_ROLLOUT_GRAPH=1; the pipeline's scratch is
+  // owned by the rollouts object, so the graph holds only kernels, memsets and event edges), but
+  // replay measured erratic (67-138 M ego-frames/s run to run on one B200) where direct issue
+  // gives 123-144 M, so direct issue is the default.
+  const bool use_graph = n_ticks >= 8 && getenv("PP_ROLLOUT_GRAPH") != nullptr;
   if (use_graph) {
     cudaStream_t caller = st;
     cudaEventRecord(r->o_fork, caller);

@@ -90,7 +90,11 @@ def test_rollout_groups_and_graph_replay_match_cpu_model(pp, oracle):
     m = pp.Map()
     a = pp.Rollouts(m, n, c, seed=seed)
     b = pp.Rollouts(m, n, c, seed=seed)
-    a.run(ticks, k)            # >= 8 ticks: one direct tick, then graph replays
+    os.environ["PP_ROLLOUT_GRAPH"] = "1"
+    try:
+        a.run(ticks, k)        # >= 8 ticks: one direct tick, then graph replays
+    finally:
+        del os.environ["PP_ROLLOUT_GRAPH"]
     for _ in range(ticks):
         b.run(1, k)            # direct issue
     sa, sb = a.state(), b.state()
