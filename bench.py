@@ -451,6 +451,19 @@ def main():
         kernels = [{"name": nm, "ms_per_step": ms, "share": ms / pipe_ms if pipe_ms else None,
                     "launches_per_step": phase_chunks // args.steps if nm[0] == "k" else None}
                    for nm, ms in zip(names, phase_ms)]
+        # the dominant kernel on its own: algorithmic bytes it must move per frame
+        own_bytes = {"k_prep": 204.0, "k_cars": 36.0 * args.cars, "k_decide": 160.0 + 76.0,
+                     "k_emit": 640.0 + 8.0}
+        dom = max(kernels[:4], key=lambda k: k["ms_per_step"])
+        dom_launches = max(1, phase_chunks // args.steps)
+        dom_ms = dom["ms_per_step"] / dom_launches
+        dom_bytes = own_bytes[dom["name"]] * n / dom_launches
+        dominant = {"kernel": dom["name"], "ms_per_launch": dom_ms, "launches_per_step": dom_launches,
+                    "algorithmic_bytes_per_frame": own_bytes[dom["name"]],
+                    "algorithmic_bytes_per_launch": dom_bytes,
+                    "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "unit": "GB/s",
+                    "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak,
+                    "traffic": traffic_by_kernel.get(dom["name"])}
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -472,7 +485,7 @@ def main():
                          "kernel": "pp_plan_batch pipeline (k_prep + k_cars + k_decide + k_emit, "
                                    "4 chunks of 262,144 frames per step); dominant: "
                                    + max(kernels[:4], key=lambda k: k["ms_per_step"])["name"],
-                         "kernel_ms": kern_ms, "kernels": kernels,
+                         "kernel_ms": kern_ms, "kernels": kernels, "dominant_kernel": dominant,
                          "algorithmic_bytes_per_frame": bytes_in + BYTES_OUT,
                          "algorithmic_bytes_per_step": alg_bytes,
                          "note": "FP64-issue / divergence bound, not HBM bound (DESIGN.md §2): "
