@@ -379,7 +379,6 @@ def main():
     k_stop = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = pp.launch_count()
-    pp.set_phase_timing(True)   # CUDA events around every kernel of the pipeline (same stream)
     fence()
     ev0.record(stream)
     for i in range(args.steps):
@@ -393,9 +392,19 @@ def main():
     fence()
     launches = pp.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
+    # Per-kernel breakdown: in the timed region four chunks are in flight at once, so a kernel's
+    # own duration cannot be read there.  A few extra (untimed) steps run the same launches
+    # strictly one after the other with CUDA events around each kernel.
+    pp.set_pipes(1)
+    pp.set_phase_timing(True)
+    bd_steps = 3
+    for _ in range(bd_steps):
+        pp.plan_batch(m, df, dp)
     phase_ms, phase_chunks = pp.get_phase_ms()
     pp.set_phase_timing(False)
-    phase_ms = [v / args.steps for v in phase_ms]
+    pp.set_pipes(0)
+    phase_ms = [v / bd_steps for v in phase_ms]
+    phase_chunks //= bd_steps
     total_ms = ev0.elapsed_time(ev1)
     kern_ms = sum(a.elapsed_time(b) for a, b in zip(k_start, k_stop)) / args.steps
     t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device="cuda")
@@ -447,20 +456,15 @@ def main():
             except Exception:
                 traffic, traffic_by_kernel = None, {}
         names = ["k_prep", "k_cars", "k_decide", "k_emit", "side-stream tail (k_fallback/k_slow join)"]
-        # Chunks run on several internal streams at once, so a kernel's event-to-event time
-        # includes the kernels of other chunks sharing the GPU with it: the shares are taken from
-        # those times and applied to the measured duration of the whole pp_plan_batch.
         pipe_ms = sum(phase_ms)
-        kernels = [{"name": nm, "share": ms / pipe_ms if pipe_ms else None,
-                    "ms_per_step": kern_ms * ms / pipe_ms if pipe_ms else None,
-                    "ms_per_step_overlapped": ms,
-                    "launches_per_step": phase_chunks // args.steps if nm[0] == "k" else None}
+        kernels = [{"name": nm, "ms_per_step": ms, "share": ms / pipe_ms if pipe_ms else None,
+                    "launches_per_step": phase_chunks if nm[0] == "k" else None}
                    for nm, ms in zip(names, phase_ms)]
         # the dominant kernel on its own: algorithmic bytes it must move per frame
         own_bytes = {"k_prep": 204.0, "k_cars": 36.0 * args.cars, "k_decide": 160.0 + 76.0,
                      "k_emit": 640.0 + 8.0}
         dom = max(kernels[:4], key=lambda k: k["ms_per_step"])
-        dom_launches = max(1, phase_chunks // args.steps)
+        dom_launches = max(1, phase_chunks)
         dom_ms = dom["ms_per_step"] / dom_launches
         dom_bytes = own_bytes[dom["name"]] * n / dom_launches
         dominant = {"kernel": dom["name"], "ms_per_launch": dom_ms, "launches_per_step": dom_launches,
@@ -492,6 +496,7 @@ def main():
                                    "dominant: "
                                    + max(kernels[:4], key=lambda k: k["ms_per_step"])["name"],
                          "kernel_ms": kern_ms, "kernels": kernels, "dominant_kernel": dominant,
+                         "kernels_one_after_the_other_ms": pipe_ms,
                          "algorithmic_bytes_per_frame": bytes_in + BYTES_OUT,
                          "algorithmic_bytes_per_step": alg_bytes,
                          "note": "FP64-issue / divergence bound, not HBM bound (DESIGN.md §2): "

@@ -38,7 +38,7 @@ EXPORTS = [
     "pp_project_speed_batch",
     "pp_dev_alloc", "pp_dev_free", "pp_dev_upload", "pp_dev_download", "pp_dev_sync",
     "pp_rollouts_create", "pp_rollouts_destroy", "pp_rollouts_run", "pp_rollouts_last",
-    "pp_rollouts_get_state", "pp_rollouts_stats", "pp_sweep_batch",
+    "pp_rollouts_get_state", "pp_rollouts_stats", "pp_sweep_batch", "pp_set_pipes",
 ]
 
 
@@ -78,6 +78,10 @@ def device_count() -> int:
 
 def set_kernel_variant(v: int):
     _check(lib.pp_set_kernel_variant(C.c_int(v)), "pp_set_kernel_variant")
+
+
+def set_pipes(n: int):
+    _check(lib.pp_set_pipes(C.c_int(n)), "pp_set_pipes")
 
 
 def set_phase_timing(on: bool):

@@ -27,7 +27,7 @@
 // double-buffered, stream-ordered scratch in HBM.  The ncu evidence behind each
 // cut is in profiles/ (r1_v0: the single fused kernel, 45 % instruction-fetch
 // stalls on 155 KB of SASS at 15 of 32 lanes; r1b/r1c: the division of the
-// interior step at 4 lanes, the library atan2 at 3.6 lanes, knot staging; r1h:
+// interior step at 4 lanes, the library atan2 at 3.6 lanes, knot staging; r1j:
 // the current state).  The fused single-kernel form is kept as variant 1: it
 // has the lowest latency for small batches and is the bitwise cross-check of
 // the pipeline (tests/test_gpu_parity.py).
@@ -1041,9 +1041,10 @@ static int64_t pipe_chunk() {
   static const int64_t v = env_int("PP_PIPE_CHUNK", (int)kPipeChunk, 4096, 1 << 22);
   return v;
 }
+static int g_pipes_override = 0;  // pp_set_pipes
 static int pipe_count() {
   static const int v = env_int("PP_PIPES", 4, 1, kMaxPipes);
-  return v;
+  return g_pipes_override > 0 ? g_pipes_override : v;
 }
 
 // Bytes of scratch the pipeline needs for a batch (0 for batches the fused kernel takes).
@@ -1232,6 +1233,12 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
   if (!caller_scratch) cudaFreeAsync(buf, st);
   if (rc == PP_OK) rc = check_launch("plan pipeline join");
   return rc;
+}
+
+extern "C" int pp_set_pipes(int pipes) {
+  if (pipes < 0 || pipes > kMaxPipes) return PP_E_RANGE;
+  g_pipes_override = pipes;
+  return PP_OK;
 }
 
 extern "C" int pp_set_phase_timing(int on) {

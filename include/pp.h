@@ -200,6 +200,10 @@ int pp_stats_batch(const pp_plans *plans_dev, int64_t n_frames, int64_t *stats_d
 /* Kernel selection for pp_plan_batch: 0 = auto (pipeline; the fused kernel for
  * batches under 4096 frames), 1 = fused single kernel, 2 = pipeline. */
 int pp_set_kernel_variant(int variant);
+/* Chunks of a large batch that pp_plan_batch keeps in flight at once on internal streams:
+ * 1..8, 0 = default (4).  1 runs the kernels of the pipeline strictly one after the other,
+ * which is what a per-kernel time breakdown needs. */
+int pp_set_pipes(int pipes);
 /* Measurement aid (bench.py): when on, pp_plan_batch records CUDA events on the
  * caller's stream around each kernel of the pipeline.  pp_get_phase_ms waits for
  * the last of them and returns the summed device time in ms of ms_out[0] = ego
