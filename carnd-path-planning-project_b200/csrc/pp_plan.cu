@@ -1037,9 +1037,17 @@ extern "C" int pp_set_kernel_variant(int variant) {
 }
 
 // frames per chunk and chunks in flight (PP_PIPE_CHUNK / PP_PIPES: tuning experiments)
-static int64_t pipe_chunk() {
-  static const int64_t v = env_int("PP_PIPE_CHUNK", (int)kPipeChunk, 4096, 1 << 22);
-  return v;
+static int pipe_count();
+// frames per chunk for a batch of n: at most PP_PIPE_CHUNK (262,144), and small enough that a
+// mid-sized batch still splits into one chunk per pipe (but not below 32,768 frames)
+static int64_t chunk_for(int64_t n) {
+  static const int64_t cap = env_int("PP_PIPE_CHUNK", (int)kPipeChunk, 4096, 1 << 22);
+  const int64_t floor_ = 32768 < cap ? 32768 : cap;
+  int64_t c = (n + pipe_count() - 1) / pipe_count();
+  c = (c + 1023) / 1024 * 1024;
+  if (c < floor_) c = floor_;
+  if (c > cap) c = cap;
+  return c < n ? c : n;
 }
 static int g_pipes_override = 0;  // pp_set_pipes
 static int pipe_count() {
@@ -1050,7 +1058,7 @@ static int pipe_count() {
 // Bytes of scratch the pipeline needs for a batch (0 for batches the fused kernel takes).
 size_t ppi::plan_scratch_bytes(int64_t n_frames, int max_cars) {
   if (n_frames <= 0 || g_variant == 1 || (g_variant == 0 && n_frames < kFusedBelow)) return 0;
-  const int64_t chunk = n_frames < pipe_chunk() ? n_frames : pipe_chunk();
+  const int64_t chunk = chunk_for(n_frames);
   const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
   const int n_buf = (int)(n_chunks < pipe_count() ? n_chunks : pipe_count());
   const size_t scratch = (scratch_bytes(chunk, max_cars) + 255) & ~(size_t)255;
@@ -1108,7 +1116,7 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
   }
 
   const int mc = in->max_cars;
-  const int64_t chunk = n_frames < pipe_chunk() ? n_frames : pipe_chunk();
+  const int64_t chunk = chunk_for(n_frames);
   {  // keep freed scratch inside the stream-ordered pool (default threshold 0 hands it back to
      // the driver at every synchronisation, which costs milliseconds per call)
     static bool pool_tuned[64] = {false};
