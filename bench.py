@@ -150,7 +150,7 @@ def run_rollouts(args):
     pp = load_package()
     m = pp.Map()
     n, ticks = args.rollouts, args.ticks
-    ro = pp.Rollouts(m, n, args.cars, seed=SEED, first=rank * n)
+    ro = pp.Rollouts(m, n, args.cars, seed=SEED, first=rank * n, lean=True)
     ro.run(max(3, min(20, ticks)), args.consume_k)  # warm-up ticks (also leaves the cold start)
     torch.cuda.synchronize()
     if world > 1:

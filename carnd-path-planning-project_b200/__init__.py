@@ -38,7 +38,8 @@ EXPORTS = [
     "pp_project_speed_batch",
     "pp_dev_alloc", "pp_dev_free", "pp_dev_upload", "pp_dev_download", "pp_dev_sync",
     "pp_rollouts_create", "pp_rollouts_destroy", "pp_rollouts_run", "pp_rollouts_last",
-    "pp_rollouts_get_state", "pp_rollouts_stats", "pp_sweep_batch", "pp_set_pipes",
+    "pp_rollouts_get_state", "pp_rollouts_stats", "pp_rollouts_set_lean", "pp_sweep_batch",
+    "pp_set_pipes",
 ]
 
 
@@ -262,11 +263,14 @@ class RolloutStateHost:
 class Rollouts:
     """Closed-loop rollouts (BASELINE config 3): pp_rollouts_* of include/pp.h."""
 
-    def __init__(self, m: Map, n: int, n_cars: int = 12, seed: int = 0x5EED, first: int = 0):
+    def __init__(self, m: Map, n: int, n_cars: int = 12, seed: int = 0x5EED, first: int = 0,
+                 lean: bool = False):
         self.map, self.n, self.n_cars = m, n, n_cars
         self._h = C.c_void_p()
         _check(lib.pp_rollouts_create(m.handle, C.c_int64(n), C.c_int32(n_cars), C.c_uint64(seed),
                                       C.c_int64(first), C.byref(self._h)), "pp_rollouts_create")
+        if lean:
+            _check(lib.pp_rollouts_set_lean(self._h, C.c_int(1)), "pp_rollouts_set_lean")
 
     def run(self, ticks: int, consume_k: int = 1, cfg: Config | None = None, stream=None):
         import torch
@@ -297,8 +301,9 @@ class Rollouts:
         pb = PlanBatch(self.n, mc, diag=True, cars=True)
         for name, _, _ in abi.PLAN_FIELDS:
             arr = getattr(pb, name)
-            _check(lib.pp_dev_download(C.c_void_p(arr.ctypes.data), C.c_void_p(getattr(ps, name)),
-                                       C.c_size_t(arr.nbytes)), "pp_dev_download")
+            if getattr(ps, name):  # lean rollouts leave the diagnostics out
+                _check(lib.pp_dev_download(C.c_void_p(arr.ctypes.data), C.c_void_p(getattr(ps, name)),
+                                           C.c_size_t(arr.nbytes)), "pp_dev_download")
         return fb, pb
 
     def stats(self, stream=None):

@@ -1040,10 +1040,10 @@ extern "C" int pp_set_kernel_variant(int variant) {
 static int pipe_count();
 // frames per chunk for a batch of n: at most PP_PIPE_CHUNK (262,144), and small enough that a
 // mid-sized batch still splits into one chunk per pipe (but not below 32,768 frames)
-static int64_t chunk_for(int64_t n) {
+static int64_t chunk_for(int64_t n, int pipes) {
   static const int64_t cap = env_int("PP_PIPE_CHUNK", (int)kPipeChunk, 4096, 1 << 22);
   const int64_t floor_ = 32768 < cap ? 32768 : cap;
-  int64_t c = (n + pipe_count() - 1) / pipe_count();
+  int64_t c = (n + pipes - 1) / pipes;
   c = (c + 1023) / 1024 * 1024;
   if (c < floor_) c = floor_;
   if (c > cap) c = cap;
@@ -1056,11 +1056,12 @@ static int pipe_count() {
 }
 
 // Bytes of scratch the pipeline needs for a batch (0 for batches the fused kernel takes).
+// (a caller that brings its own scratch drives its own concurrency: one chunk in flight)
 size_t ppi::plan_scratch_bytes(int64_t n_frames, int max_cars) {
   if (n_frames <= 0 || g_variant == 1 || (g_variant == 0 && n_frames < kFusedBelow)) return 0;
-  const int64_t chunk = chunk_for(n_frames);
+  const int64_t chunk = chunk_for(n_frames, 1);
   const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
-  const int n_buf = (int)(n_chunks < pipe_count() ? n_chunks : pipe_count());
+  const int n_buf = 1;
   const size_t scratch = (scratch_bytes(chunk, max_cars) + 255) & ~(size_t)255;
   return n_buf * scratch + (size_t)n_frames * 2 * sizeof(int32_t) +
          (size_t)n_chunks * 2 * sizeof(int32_t) + 256;
@@ -1116,7 +1117,8 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
   }
 
   const int mc = in->max_cars;
-  const int64_t chunk = chunk_for(n_frames);
+  const int max_pipes = caller_scratch ? 1 : pipe_count();
+  const int64_t chunk = chunk_for(n_frames, max_pipes);
   {  // keep freed scratch inside the stream-ordered pool (default threshold 0 hands it back to
      // the driver at every synchronisation, which costs milliseconds per call)
     static bool pool_tuned[64] = {false};
@@ -1135,7 +1137,7 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
   // Chunks are planned on `pipes` internal streams at once (see Pipes); a single chunk runs on
   // the caller's stream.  Every pipe has its own scratch buffer and its own side stream.
   const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
-  const int pipes = (int)(n_chunks < pipe_count() ? n_chunks : pipe_count());
+  const int pipes = (int)(n_chunks < max_pipes ? n_chunks : max_pipes);
   Pipes &pp_ = t_pipes;
   if (pipes > 1 && pp_.ensure() != PP_OK) return check_launch("pipe streams");
   cudaStream_t lane_st[kMaxPipes];

@@ -21,8 +21,10 @@ struct pp_rollouts {
   int64_t tick = 0;
   char *buf = nullptr;  // one device allocation
   // simulator state
-  double *ego_x, *ego_y, *ego_yaw, *ego_mph, *path_x, *path_y, *car_ratio, *car_speed;
-  int32_t *path_n, *target_lane, *car_lane, *car_wp;
+  double *ego_x, *ego_y, *ego_yaw, *ego_mph, *car_ratio, *car_speed;
+  int32_t *path_n, *path_off, *target_lane, *car_lane, *car_wp;
+  bool lean = false;  // plans without the per-frame diagnostics and unused per-car outputs
+  pp_plans full_pl;   // the complete set of output pointers (restored when lean is switched off)
   // per-tick frames and plans
   pp_frames fr;
   pp_plans pl;
@@ -67,8 +69,11 @@ struct Track {
   int n;
   int stride;
   __host__ __device__ const double *row(int i) const {
-    int k = i % n;
-    if (k < 0) k += n;
+    int k = i;
+    if ((unsigned)i >= (unsigned)n) {  // the simulator keeps indices in [0, n): rarely taken
+      k = i % n;
+      if (k < 0) k += n;
+    }
     return t + (size_t)k * stride;
   }
   __host__ __device__ double len(int w, int lane) const { return row(w)[10 + lane]; }
@@ -114,122 +119,77 @@ struct Track {
   }
 };
 
-// frame <- state (one thread per rollout)
+// Simulator state on the device (per rollout unless noted).  The unconsumed points of the last
+// plan are not copied anywhere: they stay in the plan buffer and `path_off` says where they start.
+struct SimState {
+  double *ego_x, *ego_y, *ego_yaw, *ego_mph;
+  int32_t *path_n, *path_off, *target_lane;
+  int32_t *car_lane, *car_wp;       // [R][C]
+  double *car_ratio, *car_speed;    // [R][C]
+  int64_t *ticks;
+};
+
+// frame <- state.  A block owns kB consecutive rollouts: one thread per rollout writes the ego
+// part, then the block's threads sweep the rollouts' car slots (coalesced).
 __global__ void __launch_bounds__(kB)
-k_sim_frames(Track trk, int64_t lo, int64_t n, int c, const double *ego_x, const double *ego_y,
-             const double *ego_yaw, const double *ego_mph, const int32_t *path_n,
-             const double *path_x, const double *path_y, const int32_t *target_lane,
-             const int32_t *car_lane, const int32_t *car_wp, const double *car_ratio,
-             const double *car_speed, pp_frames fr) {
-  const int64_t r = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= lo + n) return;
-  const_cast<double *>(fr.ego_x)[r] = ego_x[r];
-  const_cast<double *>(fr.ego_y)[r] = ego_y[r];
-  const_cast<double *>(fr.ego_yaw_deg)[r] = ego_yaw[r];
-  const_cast<double *>(fr.ego_speed_mph)[r] = ego_mph[r];
-  const int pn = path_n[r];
-  const_cast<int32_t *>(fr.prev_n)[r] = pn;
-  for (int i = 0; i < PP_PREV_KEEP; i++) {
-    const bool have = i < pn;
-    const_cast<double *>(fr.prev_x)[r * PP_PREV_KEEP + i] = have ? path_x[r * PP_PATH_LEN + i] : 0.0;
-    const_cast<double *>(fr.prev_y)[r * PP_PREV_KEEP + i] = have ? path_y[r * PP_PATH_LEN + i] : 0.0;
+k_sim_frames(Track trk, int64_t lo, int64_t n, int c, SimState st, pp_plans pl, pp_frames fr) {
+  const int64_t r0 = lo + (int64_t)blockIdx.x * blockDim.x;
+  const int64_t r = r0 + threadIdx.x;
+  if (r < lo + n) {
+    const_cast<double *>(fr.ego_x)[r] = st.ego_x[r];
+    const_cast<double *>(fr.ego_y)[r] = st.ego_y[r];
+    const_cast<double *>(fr.ego_yaw_deg)[r] = st.ego_yaw[r];
+    const_cast<double *>(fr.ego_speed_mph)[r] = st.ego_mph[r];
+    const int pn = st.path_n[r];
+    const_cast<int32_t *>(fr.prev_n)[r] = pn;
+    const double *nx = pl.next_x + r * PP_PATH_LEN + st.path_off[r];
+    const double *ny = pl.next_y + r * PP_PATH_LEN + st.path_off[r];
+    for (int i = 0; i < PP_PREV_KEEP; i++) {
+      const bool have = i < pn;
+      const_cast<double *>(fr.prev_x)[r * PP_PREV_KEEP + i] = have ? nx[i] : 0.0;
+      const_cast<double *>(fr.prev_y)[r * PP_PREV_KEEP + i] = have ? ny[i] : 0.0;
+    }
+    const_cast<int32_t *>(fr.target_lane_in)[r] = st.target_lane[r];
+    const_cast<int32_t *>(fr.n_cars)[r] = c;
   }
-  const_cast<int32_t *>(fr.target_lane_in)[r] = target_lane[r];
-  const_cast<int32_t *>(fr.n_cars)[r] = c;
-  for (int j = 0; j < c; j++) {
-    const int64_t k = r * c + j;
+  int64_t r_end = r0 + blockDim.x;
+  if (r_end > lo + n) r_end = lo + n;
+  for (int64_t q = r0 * c + threadIdx.x; q < r_end * c; q += blockDim.x) {
     double x, y, vx, vy;
-    trk.car(car_lane[k], car_wp[k], car_ratio[k], car_speed[k], x, y, vx, vy);
-    const_cast<int32_t *>(fr.car_id)[k] = j;
-    const_cast<double *>(fr.car_x)[k] = x;
-    const_cast<double *>(fr.car_y)[k] = y;
-    const_cast<double *>(fr.car_vx)[k] = vx;
-    const_cast<double *>(fr.car_vy)[k] = vy;
+    trk.car(st.car_lane[q], st.car_wp[q], st.car_ratio[q], st.car_speed[q], x, y, vx, vy);
+    const_cast<int32_t *>(fr.car_id)[q] = (int32_t)(q % c);
+    const_cast<double *>(fr.car_x)[q] = x;
+    const_cast<double *>(fr.car_y)[q] = y;
+    const_cast<double *>(fr.car_vx)[q] = vx;
+    const_cast<double *>(fr.car_vy)[q] = vy;
   }
 }
 
-__device__ __forceinline__ void sim_advance_one(
-    const Track &trk, int64_t r, int c, uint64_t seed, int64_t first, int64_t *__restrict__ ticks,
-    int consume_k, double *ego_x, double *ego_y, double *ego_mph, int32_t *path_n, double *path_x,
-    double *path_y, int32_t *target_lane, int32_t *car_lane, int32_t *car_wp, double *car_ratio,
-    double *car_speed, const pp_plans &pl);
-
-// state <- simulator step(plan) (one thread per rollout), and this tick's statistics
+// state <- simulator step(plan), and this tick's contribution to the aggregate statistics
+// (definition: pp_stats_batch).  Same block layout: the car slots first (they read the rollout's
+// tick before it is counted), then one thread per rollout for the ego; the trajectory checksum
+// is taken by the warp over its 32 rollouts' rows with coalesced loads.
 __global__ void __launch_bounds__(kB)
-k_sim_advance(Track trk, int64_t lo, int64_t n, int c, uint64_t seed, int64_t first,
-              int64_t *__restrict__ ticks, int consume_k,
-              double *ego_x, double *ego_y, double *ego_mph, int32_t *path_n, double *path_x,
-              double *path_y, int32_t *target_lane, int32_t *car_lane, int32_t *car_wp,
-              double *car_ratio, double *car_speed, pp_plans pl, unsigned long long *stats_sum) {
+k_sim_advance(Track trk, int64_t lo, int64_t n, int c, uint64_t seed, int64_t first, int consume_k,
+              SimState st, pp_plans pl, unsigned long long *stats_sum) {
   __shared__ unsigned long long s_acc[PP_STATS_LEN];
   for (int i = threadIdx.x; i < PP_STATS_LEN; i += blockDim.x) s_acc[i] = 0;
-  __syncthreads();
-  const int64_t r = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < lo + n) {
-    // ---- this tick's contribution to the aggregate statistics (definition: pp_stats_batch)
-    {
-      const int np = pl.n_points[r];
-      const int tl = pl.target_lane[r], el = pl.ego_lane[r];
-      const uint32_t fl = pl.flags[r];
-      long long xs = 0;
-      for (int i = 0; i < np; i++) {
-        const double x = pl.next_x[r * PP_PATH_LEN + i], y = pl.next_y[r * PP_PATH_LEN + i];
-        if (x == x && y == y && fabs(x) < 1e12 && fabs(y) < 1e12)
-          xs += (long long)(x * 256.0) + (long long)(y * 256.0);
-      }
-      atomicAdd(&s_acc[PP_STAT_FRAMES], 1ull);
-      atomicAdd(&s_acc[PP_STAT_POINTS], (unsigned long long)np);
-      if (tl >= 0 && tl < 3) atomicAdd(&s_acc[PP_STAT_TARGET_LANE0 + tl], 1ull);
-      if (el >= 0 && el < 3) atomicAdd(&s_acc[PP_STAT_EGO_LANE0 + el], 1ull);
-      if (tl != el) atomicAdd(&s_acc[PP_STAT_LANE_CHANGES], 1ull);
-      for (int b = 0; b < PP_NUM_FLAGS; b++)
-        if (fl & (1u << b)) atomicAdd(&s_acc[PP_STAT_FLAG0 + b], 1ull);
-      if (xs) atomicAdd(&s_acc[PP_STAT_XSUM], (unsigned long long)xs);
-    }
-    sim_advance_one(trk, r, c, seed, first, ticks, consume_k, ego_x, ego_y, ego_mph, path_n, path_x,
-                    path_y, target_lane, car_lane, car_wp, car_ratio, car_speed, pl);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < PP_STATS_LEN; i += blockDim.x)
-    if (s_acc[i]) atomicAdd(&stats_sum[i], s_acc[i]);
-}
-
-__device__ __forceinline__ void sim_advance_one(
-    const Track &trk, int64_t r, int c, uint64_t seed, int64_t first, int64_t *__restrict__ ticks,
-    int consume_k, double *ego_x, double *ego_y, double *ego_mph, int32_t *path_n, double *path_x,
-    double *path_y, int32_t *target_lane, int32_t *car_lane, int32_t *car_wp, double *car_ratio,
-    double *car_speed, const pp_plans &pl) {
-  const int64_t tick = ticks[r];  // every rollout counts its own ticks (all equal)
-  ticks[r] = tick + 1;
-  // ---- the ego consumes k points of the new trajectory
-  const int np = pl.n_points[r];
-  const int k = consume_k < np ? consume_k : np;
-  const double *nx = pl.next_x + r * PP_PATH_LEN, *ny = pl.next_y + r * PP_PATH_LEN;
-  if (k > 0) {
-    const double ox = ego_x[r], oy = ego_y[r];
-    const double qx = nx[k - 1], qy = ny[k - 1];
-    const double d = sqrt((qx - ox) * (qx - ox) + (qy - oy) * (qy - oy));
-    ego_x[r] = qx;
-    ego_y[r] = qy;
-    ego_mph[r] = d / (kTick * k) * 2.237;
-  }
-  for (int i = 0; i < PP_PATH_LEN; i++) {
-    const bool have = i + k < np;
-    path_x[r * PP_PATH_LEN + i] = have ? nx[i + k] : 0.0;
-    path_y[r * PP_PATH_LEN + i] = have ? ny[i + k] : 0.0;
-  }
-  path_n[r] = np - k;
-  target_lane[r] = pl.target_lane[r];
-  // ---- traffic
-  const double dt = kTick * (k > 0 ? k : 1);
-  const int ref_wp = pl.ref_wp[r];
-  for (int j = 0; j < c; j++) {
-    const int64_t q = r * c + j;
-    int lane = car_lane[q], w = car_wp[q];
-    double u = car_ratio[q], v = car_speed[q];
+  const int64_t r0 = lo + (int64_t)blockIdx.x * blockDim.x;
+  int64_t r_end = r0 + blockDim.x;
+  if (r_end > lo + n) r_end = lo + n;
+  // ---- traffic (one thread per car slot)
+  for (int64_t q = r0 * c + threadIdx.x; q < r_end * c; q += blockDim.x) {
+    const int64_t r = q / c;
+    const int j = (int)(q - r * c);
+    const int np = pl.n_points[r];
+    const int k = consume_k < np ? consume_k : np;
+    const double dt = kTick * (k > 0 ? k : 1);
+    int lane = st.car_lane[q], w = st.car_wp[q];
+    double u = st.car_ratio[q], v = st.car_speed[q];
     const int m_lane = pl.car_lane[q];
     const double m_s = pl.car_s[q];
     if (m_lane < 0 || m_s < -100.0 || m_s > 300.0) {  // respawn
+      const int64_t tick = st.ticks[r];
       const uint64_t key = mix64(mix64(seed ^ 0x5157ull) ^ ((uint64_t)(first + r) * 0xD1B54A32D192ED03ull));
       const uint64_t h = mix64(key ^ ((uint64_t)tick * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)j << 48));
       const double u1 = u01(mix64(h + 1)), u2 = u01(mix64(h + 2)), u3 = u01(mix64(h + 3));
@@ -237,7 +197,7 @@ __device__ __forceinline__ void sim_advance_one(
       lane = (int)(3.0 * u2);
       if (lane > 2) lane = 2;
       v = 17.88 + 8.94 * u3;
-      w = ref_wp;
+      w = pl.ref_wp[r];
       u = 0.5;
       trk.walk(w, u, lane, ds);
     } else {  // constant speed along the lane centre line
@@ -248,11 +208,62 @@ __device__ __forceinline__ void sim_advance_one(
         u = left / trk.len(w, lane);
       }
     }
-    car_lane[q] = lane;
-    car_wp[q] = w;
-    car_ratio[q] = u;
-    car_speed[q] = v;
+    st.car_lane[q] = lane;
+    st.car_wp[q] = w;
+    st.car_ratio[q] = u;
+    st.car_speed[q] = v;
   }
+  __syncthreads();
+  // ---- the ego consumes k points of the new trajectory (one thread per rollout)
+  const int64_t r = r0 + threadIdx.x;
+  const bool live = r < lo + n;
+  int np = 0;
+  if (live) {
+    np = pl.n_points[r];
+    const int k = consume_k < np ? consume_k : np;
+    if (k > 0) {
+      const double ox = st.ego_x[r], oy = st.ego_y[r];
+      const double qx = pl.next_x[r * PP_PATH_LEN + k - 1], qy = pl.next_y[r * PP_PATH_LEN + k - 1];
+      const double d = sqrt((qx - ox) * (qx - ox) + (qy - oy) * (qy - oy));
+      st.ego_x[r] = qx;
+      st.ego_y[r] = qy;
+      st.ego_mph[r] = d / (kTick * k) * 2.237;
+    }
+    st.path_n[r] = np - k;
+    st.path_off[r] = k;
+    const int tl = pl.target_lane[r], el = pl.ego_lane[r];
+    st.target_lane[r] = tl;
+    st.ticks[r] += 1;
+    const uint32_t fl = pl.flags[r];
+    atomicAdd(&s_acc[PP_STAT_FRAMES], 1ull);
+    atomicAdd(&s_acc[PP_STAT_POINTS], (unsigned long long)np);
+    if (tl >= 0 && tl < 3) atomicAdd(&s_acc[PP_STAT_TARGET_LANE0 + tl], 1ull);
+    if (el >= 0 && el < 3) atomicAdd(&s_acc[PP_STAT_EGO_LANE0 + el], 1ull);
+    if (tl != el) atomicAdd(&s_acc[PP_STAT_LANE_CHANGES], 1ull);
+    for (int b = 0; b < PP_NUM_FLAGS; b++)
+      if (fl & (1u << b)) atomicAdd(&s_acc[PP_STAT_FLAG0 + b], 1ull);
+  }
+  {  // checksum: the warp walks its 32 rollouts' rows together
+    const int ln = threadIdx.x & 31;
+    const int64_t wr0 = r0 + (threadIdx.x & ~31);
+    long long xs = 0;
+    for (int rr = 0; rr < 32; rr++) {
+      const int np_r = __shfl_sync(0xffffffffu, np, rr);
+      const int64_t base = (wr0 + rr) * PP_PATH_LEN;
+      for (int i = ln; i < np_r; i += 32) {
+        const double x = pl.next_x[base + i], y = pl.next_y[base + i];
+        if (x == x && y == y && fabs(x) < 1e12 && fabs(y) < 1e12)
+          xs += (long long)(x * 256.0) + (long long)(y * 256.0);
+      }
+    }
+    unsigned long long v = (unsigned long long)xs;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (ln == 0 && v) atomicAdd(&s_acc[PP_STAT_XSUM], v);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PP_STATS_LEN; i += blockDim.x)
+    if (s_acc[i]) atomicAdd(&stats_sum[i], s_acc[i]);
 }
 
 inline size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -290,7 +301,7 @@ extern "C" int pp_rollouts_create(const pp_map *map, int64_t n, int32_t c, uint6
     return o;
   };
   const size_t o_ex = take(N * 8), o_ey = take(N * 8), o_yaw = take(N * 8), o_mph = take(N * 8);
-  const size_t o_pn = take(N * 4), o_px = take(N * PP_PATH_LEN * 8), o_py = take(N * PP_PATH_LEN * 8);
+  const size_t o_pn = take(N * 4), o_po = take(N * 4);
   const size_t o_tl = take(N * 4), o_cl = take(NC * 4), o_cw = take(NC * 4), o_cr = take(NC * 8),
                o_cs = take(NC * 8);
   // frames
@@ -320,8 +331,7 @@ extern "C" int pp_rollouts_create(const pp_map *map, int64_t n, int32_t c, uint6
   r->ego_yaw = (double *)(b + o_yaw);
   r->ego_mph = (double *)(b + o_mph);
   r->path_n = (int32_t *)(b + o_pn);
-  r->path_x = (double *)(b + o_px);
-  r->path_y = (double *)(b + o_py);
+  r->path_off = (int32_t *)(b + o_po);
   r->target_lane = (int32_t *)(b + o_tl);
   r->car_lane = (int32_t *)(b + o_cl);
   r->car_wp = (int32_t *)(b + o_cw);
@@ -484,9 +494,9 @@ int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStre
     const int grid = (int)((cnt + kB - 1) / kB);
     const pp_frames fr = ppi::offset_frames(r->fr, lo);
     const pp_plans pl = ppi::offset_plans(r->pl, lo, mc);
-    k_sim_frames<<<grid, kB, 0, gs>>>(trk, lo, cnt, r->c, r->ego_x, r->ego_y, r->ego_yaw, r->ego_mph,
-                                      r->path_n, r->path_x, r->path_y, r->target_lane, r->car_lane,
-                                      r->car_wp, r->car_ratio, r->car_speed, r->fr);
+    const SimState sst{r->ego_x, r->ego_y, r->ego_yaw, r->ego_mph, r->path_n, r->path_off,
+                       r->target_lane, r->car_lane, r->car_wp, r->car_ratio, r->car_speed, r->tick_dev};
+    k_sim_frames<<<grid, kB, 0, gs>>>(trk, lo, cnt, r->c, sst, r->pl, r->fr);
     if (!r->scratch[g]) {
       const size_t need = ppi::plan_scratch_bytes(per, mc);
       if (need && cudaMalloc((void **)&r->scratch[g], need) != cudaSuccess)
@@ -494,10 +504,7 @@ int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStre
     }
     int rc = ppi::plan_batch_scratch(r->map, cfg, &fr, &pl, cnt, gs, r->scratch[g]);
     if (rc != PP_OK) return rc;
-    k_sim_advance<<<grid, kB, 0, gs>>>(trk, lo, cnt, r->c, r->seed, r->first, r->tick_dev,
-                                       consume_k, r->ego_x, r->ego_y, r->ego_mph, r->path_n,
-                                       r->path_x, r->path_y, r->target_lane, r->car_lane, r->car_wp,
-                                       r->car_ratio, r->car_speed, r->pl,
+    k_sim_advance<<<grid, kB, 0, gs>>>(trk, lo, cnt, r->c, r->seed, r->first, consume_k, sst, r->pl,
                                        (unsigned long long *)r->stats_sum);
     ppi::count_launch(2);
   }
@@ -578,6 +585,27 @@ extern "C" int pp_rollouts_run(pp_rollouts *r, const pp_config *cfg, int64_t n_t
   return PP_OK;
 }
 
+extern "C" int pp_rollouts_set_lean(pp_rollouts *r, int lean) {
+  if (!r) return PP_E_ARG;
+  if (lean && !r->lean) {
+    r->full_pl = r->pl;
+    pp_plans &p = r->pl;
+    p.ego_s = p.ego_d = p.ego_vs = p.ego_vd = p.ego_speed = p.ego_acc = nullptr;
+    p.target_speed = p.target_time = nullptr;
+    p.next_car_id = p.next_car_in_target_lane = nullptr;
+    p.car_d = p.car_vs = p.car_vd = nullptr;
+    p.car_next_wp = nullptr;
+  } else if (!lean && r->lean) {
+    r->pl = r->full_pl;
+  }
+  r->lean = lean != 0;
+  if (r->graph) {  // the captured tick holds the old pointers
+    cudaGraphExecDestroy(r->graph);
+    r->graph = nullptr;
+  }
+  return PP_OK;
+}
+
 extern "C" int pp_rollouts_last(const pp_rollouts *r, pp_frames *frames_dev, pp_plans *plans_dev) {
   if (!r) return PP_E_ARG;
   if (frames_dev) *frames_dev = r->fr;
@@ -599,8 +627,20 @@ extern "C" int pp_rollouts_get_state(const pp_rollouts *r, pp_rollout_state *h) 
   dn(h->ego_yaw_deg, r->ego_yaw, N * 8);
   dn(h->ego_speed_mph, r->ego_mph, N * 8);
   dn(h->path_n, r->path_n, N * 4);
-  dn(h->path_x, r->path_x, N * PP_PATH_LEN * 8);
-  dn(h->path_y, r->path_y, N * PP_PATH_LEN * 8);
+  if (h->path_x || h->path_y) {  // the unconsumed points live in the plan buffer at path_off
+    std::vector<int32_t> pn(N), po(N);
+    std::vector<double> buf(N * PP_PATH_LEN);
+    dn(pn.data(), r->path_n, N * 4);
+    dn(po.data(), r->path_off, N * 4);
+    for (int axis = 0; axis < 2; axis++) {
+      double *dst = axis ? h->path_y : h->path_x;
+      if (!dst) continue;
+      dn(buf.data(), axis ? r->pl.next_y : r->pl.next_x, N * PP_PATH_LEN * 8);
+      for (size_t i = 0; i < N; i++)
+        for (int k = 0; k < PP_PATH_LEN; k++)
+          dst[i * PP_PATH_LEN + k] = k < pn[i] ? buf[i * PP_PATH_LEN + po[i] + k] : 0.0;
+    }
+  }
   dn(h->target_lane, r->target_lane, N * 4);
   dn(h->car_lane, r->car_lane, NC * 4);
   dn(h->car_wp, r->car_wp, NC * 4);

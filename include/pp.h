@@ -424,6 +424,10 @@ void pp_rollouts_destroy(pp_rollouts *r);
 /* n_ticks closed-loop ticks, consume_k (1..40) points per tick; asynchronous on cuda_stream. */
 int pp_rollouts_run(pp_rollouts *r, const pp_config *cfg, int64_t n_ticks, int32_t consume_k,
                     void *cuda_stream);
+/* lean != 0: the per-tick plans keep only what the simulator and the statistics read (trajectory,
+ * n_points, lanes, ref_wp, flags, per-car lane and s); the diagnostics and the other per-car
+ * outputs are not written (their pointers in pp_rollouts_last are NULL).  Default: everything. */
+int pp_rollouts_set_lean(pp_rollouts *r, int lean);
 /* Device views of the LAST tick's frames and plans (valid until the next run / destroy). */
 int pp_rollouts_last(const pp_rollouts *r, pp_frames *frames_dev, pp_plans *plans_dev);
 /* Copy the simulator state out (synchronises the device). */
