@@ -445,7 +445,7 @@ def main():
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
         # dram__bytes_read+write of the pipeline's kernels from the committed ncu capture
         # (profiles/traffic.json: bytes per 262,144-frame launch, summed over the kernels)
-        traffic, traffic_by_kernel = None, {}
+        traffic, traffic_by_kernel, ncu_view = None, {}, None
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             try:
@@ -453,8 +453,11 @@ def main():
                 traffic_by_kernel = tj.get("dram_bytes_per_launch", {})
                 per_frame = sum(traffic_by_kernel.values()) / float(tj["frames_per_launch"])
                 traffic = per_frame * n
+                # what actually bounds these kernels (ncu, each kernel alone)
+                ncu_view = {k: tj.get(k) for k in ("fp64_pipe_active_pct", "issue_active_pct",
+                                                   "active_lanes_per_warp_instr")}
             except Exception:
-                traffic, traffic_by_kernel = None, {}
+                traffic, traffic_by_kernel, ncu_view = None, {}, None
         names = ["k_prep", "k_cars", "k_decide", "k_emit", "side-stream tail (k_fallback/k_slow join)"]
         pipe_ms = sum(phase_ms)
         kernels = [{"name": nm, "ms_per_step": ms, "share": ms / pipe_ms if pipe_ms else None,
@@ -496,7 +499,7 @@ def main():
                                    "dominant: "
                                    + max(kernels[:4], key=lambda k: k["ms_per_step"])["name"],
                          "kernel_ms": kern_ms, "kernels": kernels, "dominant_kernel": dominant,
-                         "kernels_one_after_the_other_ms": pipe_ms,
+                         "kernels_one_after_the_other_ms": pipe_ms, "ncu": ncu_view,
                          "algorithmic_bytes_per_frame": bytes_in + BYTES_OUT,
                          "algorithmic_bytes_per_step": alg_bytes,
                          "note": "FP64-issue / divergence bound, not HBM bound (DESIGN.md §2): "

@@ -11,13 +11,16 @@ col = {h: i for i, h in enumerate(hdr)}
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 def num(r, k):
     return float(r[col[k]].replace(",", "") or 0)
-traffic, times = {}, {}
+traffic, times, fp64, issue, lanes = {}, {}, {}, {}, {}
 for i, r in enumerate(rows[2:]):
     name = re.search(r"(k_\w+|stats_kernel|plan_fused)", r[col["Kernel Name"]]).group(1)
     rd = num(r, "dram__bytes_read.sum") * scale[units[col["dram__bytes_read.sum"]]]
     wr = num(r, "dram__bytes_write.sum") * scale[units[col["dram__bytes_write.sum"]]]
     traffic[name] = rd + wr
     times[name] = num(r, "gpu__time_duration.sum")
+    fp64[name] = num(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")
+    issue[name] = num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active")
+    lanes[name] = num(r, "smsp__thread_inst_executed_per_inst_executed.ratio")
     txt = subprocess.run([sys.executable, os.path.join(here, "ncu_extract.py"), rep, str(i)],
                          capture_output=True, text=True).stdout
     open(os.path.join(here, f"{tag}_{name}_ncu.txt"), "w").write(txt)
@@ -26,6 +29,7 @@ json.dump({"source": f"profiles/{tag}_*_ncu.txt: ncu --set full --clock-control 
                      f"kernel over {frames} frames x 12 cars on a gpurun B200",
            "frames_per_launch": frames, "dram_bytes_per_launch": pipe,
            "stats_kernel_dram_bytes_per_launch": traffic.get("stats_kernel"),
-           "gpu_time_us_under_ncu": times},
+           "gpu_time_us_under_ncu": times,
+           "fp64_pipe_active_pct": fp64, "issue_active_pct": issue, "active_lanes_per_warp_instr": lanes},
           open(os.path.join(here, "traffic.json"), "w"), indent=1)
 print(json.dumps(traffic), sum(pipe.values()) / frames, "B/frame")
