@@ -39,7 +39,7 @@ EXPORTS = [
     "pp_dev_alloc", "pp_dev_free", "pp_dev_upload", "pp_dev_download", "pp_dev_sync",
     "pp_rollouts_create", "pp_rollouts_destroy", "pp_rollouts_run", "pp_rollouts_last",
     "pp_rollouts_get_state", "pp_rollouts_stats", "pp_rollouts_set_lean", "pp_sweep_batch",
-    "pp_set_pipes",
+    "pp_set_pipes", "pp_plan_stats_batch",
 ]
 
 
@@ -229,6 +229,22 @@ def plan_batch(m: Map, frames: DeviceFrames, plans: DevicePlans, cfg: Config | N
     _check(lib.pp_plan_batch(m.handle, C.byref(cfg), C.byref(fs), C.byref(ps),
                              C.c_int64(frames.n if n is None else n), C.c_void_p(stream)),
            "pp_plan_batch")
+
+
+def plan_stats_batch(m: Map, frames: DeviceFrames, plans: DevicePlans, cfg: Config | None = None,
+                     stream=None, out=None):
+    """pp_plan_stats_batch: plan and aggregate in one call -> int64[STATS_LEN] device tensor."""
+    import torch
+    cfg = cfg or default_config()
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    if out is None:
+        out = torch.empty(STATS_LEN, dtype=torch.int64, device=next(iter(plans.t.values())).device)
+    fs, ps = frames.struct(), plans.struct()
+    _check(lib.pp_plan_stats_batch(m.handle, C.byref(cfg), C.byref(fs), C.byref(ps),
+                                   C.c_int64(frames.n), C.c_void_p(out.data_ptr()),
+                                   C.c_void_p(stream)), "pp_plan_stats_batch")
+    return out
 
 
 def stats_batch(plans: DevicePlans, stream=None):

@@ -32,7 +32,7 @@ void set_cuda_error(const char *what, int cuda_err, const char *text);
 size_t plan_scratch_bytes(int64_t n_frames, int max_cars);
 int plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_frames *in,
                        const pp_plans *out, int64_t n_frames, void *cuda_stream,
-                       char *caller_scratch);
+                       char *caller_scratch, int64_t *stats_dev);
 
 // pp_frames / pp_plans advanced by `lo` frames
 inline pp_frames offset_frames(const pp_frames &a, int64_t lo) {

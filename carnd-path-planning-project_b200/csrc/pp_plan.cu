@@ -1005,6 +1005,12 @@ int check_launch(const char *what) {
   return PP_OK;
 }
 
+int stats_grid(int64_t n_frames) {
+  const int64_t want = (n_frames * PP_PATH_LEN + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(want < cap ? want : cap);
+}
+
 // persistent grid: enough blocks for `items`, capped at a whole number of waves
 int grid_for(int64_t items, int blocks_per_sm) {
   const int64_t want = (items + kBlock - 1) / kBlock;
@@ -1069,7 +1075,17 @@ size_t ppi::plan_scratch_bytes(int64_t n_frames, int max_cars) {
 
 extern "C" int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_frames *in,
                              const pp_plans *out, int64_t n_frames, void *cuda_stream) {
-  return ppi::plan_batch_scratch(map, cfg, in, out, n_frames, cuda_stream, nullptr);
+  return ppi::plan_batch_scratch(map, cfg, in, out, n_frames, cuda_stream, nullptr, nullptr);
+}
+
+// pp_plan_batch followed by pp_stats_batch as one call: the statistics of a chunk are taken on
+// the chunk's own internal stream as soon as it is planned, so the HBM-bound statistics pass
+// shares the GPU with the FP64-bound kernels of the other chunks instead of running alone.
+extern "C" int pp_plan_stats_batch(const pp_map *map, const pp_config *cfg, const pp_frames *in,
+                                   const pp_plans *out, int64_t n_frames, int64_t *stats_dev,
+                                   void *cuda_stream) {
+  if (!stats_dev) return PP_E_ARG;
+  return ppi::plan_batch_scratch(map, cfg, in, out, n_frames, cuda_stream, nullptr, stats_dev);
 }
 
 // pp_plan_batch with the scratch supplied by the caller (plan_scratch_bytes; nullptr: taken
@@ -1077,8 +1093,12 @@ extern "C" int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_f
 // kernel / memset / event work and can be replayed as a CUDA graph.
 int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_frames *in,
                             const pp_plans *out, int64_t n_frames, void *cuda_stream,
-                            char *caller_scratch) {
+                            char *caller_scratch, int64_t *stats_dev) {
   if (!map || !cfg || !in || !out || n_frames < 0) return PP_E_ARG;
+  if (stats_dev &&
+      cudaMemsetAsync(stats_dev, 0, PP_STATS_LEN * sizeof(int64_t), (cudaStream_t)cuda_stream) !=
+          cudaSuccess)
+    return check_launch("pp_plan_stats_batch memset");
   if (!map->dev_table) {
     ppi::set_cuda_error("pp_plan_batch: map has no device table (no usable CUDA device)", 0, "");
     return PP_E_CUDA;  // there is no CPU planning path
@@ -1113,6 +1133,11 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     plan_fused<<<grid_for(n_frames, 8), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, *in, *out,
                                                             n_frames);
     ppi::count_launch();
+    if (stats_dev) {
+      stats_kernel<<<stats_grid(n_frames), 256, 0, st>>>(*out, n_frames,
+                                                         (unsigned long long *)stats_dev);
+      ppi::count_launch();
+    }
     return check_launch("plan_fused");
   }
 
@@ -1214,6 +1239,11 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
                                                  sc.slow_qb, sc.slow_nb);
     cudaEventRecord(side.ev_done[0], side.st);
     ppi::count_launch(mc > 0 ? 6 : 5);
+    if (stats_dev) {  // this chunk's statistics, once its queued frames are planned too
+      cudaStreamWaitEvent(ls, side.ev_done[0], 0);
+      stats_kernel<<<stats_grid(cnt), 256, 0, ls>>>(fout, cnt, (unsigned long long *)stats_dev);
+      ppi::count_launch();
+    }
     rc = check_launch("plan pipeline");
     phase_mark(pe, 5, ls);
   }
@@ -1286,10 +1316,7 @@ extern "C" int pp_stats_batch(const pp_plans *p, int64_t n_frames, int64_t *stat
   if (cudaMemsetAsync(stats_dev, 0, PP_STATS_LEN * sizeof(int64_t), st) != cudaSuccess)
     return check_launch("pp_stats_batch memset");
   if (n_frames == 0) return PP_OK;
-  int64_t want = (n_frames * PP_PATH_LEN + 255) / 256;
-  int64_t cap = (int64_t)sm_count() * 8;
-  int grid = (int)(want < cap ? want : cap);
-  stats_kernel<<<grid, 256, 0, st>>>(*p, n_frames, (unsigned long long *)stats_dev);
+  stats_kernel<<<stats_grid(n_frames), 256, 0, st>>>(*p, n_frames, (unsigned long long *)stats_dev);
   ppi::count_launch();
   return check_launch("stats_kernel");
 }

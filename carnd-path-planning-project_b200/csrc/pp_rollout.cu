@@ -502,7 +502,7 @@ int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStre
       if (need && cudaMalloc((void **)&r->scratch[g], need) != cudaSuccess)
         return cuda_fail("cudaMalloc(rollout scratch)", cudaGetLastError());
     }
-    int rc = ppi::plan_batch_scratch(r->map, cfg, &fr, &pl, cnt, gs, r->scratch[g]);
+    int rc = ppi::plan_batch_scratch(r->map, cfg, &fr, &pl, cnt, gs, r->scratch[g], nullptr);
     if (rc != PP_OK) return rc;
     k_sim_advance<<<grid, kB, 0, gs>>>(trk, lo, cnt, r->c, r->seed, r->first, consume_k, sst, r->pl,
                                        (unsigned long long *)r->stats_sum);

@@ -197,6 +197,13 @@ int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const pp_frames 
 int pp_stats_batch(const pp_plans *plans_dev, int64_t n_frames, int64_t *stats_dev,
                    void *cuda_stream);
 
+/* pp_plan_batch followed by pp_stats_batch in one call (stats_dev[PP_STATS_LEN], overwritten):
+ * the statistics of each chunk are taken as soon as the chunk is planned, concurrently with
+ * the planning of the other chunks.  Same results as the two separate calls. */
+int pp_plan_stats_batch(const pp_map *map, const pp_config *cfg, const pp_frames *in,
+                        const pp_plans *out, int64_t n_frames, int64_t *stats_dev,
+                        void *cuda_stream);
+
 /* Kernel selection for pp_plan_batch: 0 = auto (pipeline; the fused kernel for
  * batches under 4096 frames), 1 = fused single kernel, 2 = pipeline. */
 int pp_set_kernel_variant(int variant);

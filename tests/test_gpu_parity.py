@@ -244,3 +244,20 @@ def test_other_maps(pp, torch_cuda, oracle, kind, n_wp):
         got = gpu_plan(pp, torch_cuda, m, fb)
         assert_plans_equal(plans_dict(got), plans_dict(want), ALL_FLAGS, bitwise_traj=False,
                            what=f"{kind}/{n_wp}/seed {seed}: ")
+
+
+@pytest.mark.parametrize("n", [700, 300000])
+def test_plan_stats_batch_equals_the_two_calls(pp, torch_cuda, gmap, n):
+    """pp_plan_stats_batch (statistics taken per chunk on the internal streams) against
+    pp_plan_batch followed by pp_stats_batch: same plans, same statistics vector."""
+    fb = pp.synth_frames(gmap, n, 12, seed=31, rare_permille=80)
+    df = pp.DeviceFrames(fb)
+    a = pp.DevicePlans(n, 12, diag=True, cars=False)
+    b = pp.DevicePlans(n, 12, diag=True, cars=False)
+    pp.plan_batch(gmap, df, a)
+    want = pp.stats_batch(a).cpu().numpy()
+    got = pp.plan_stats_batch(gmap, df, b).cpu().numpy()
+    assert np.array_equal(got, want) and got[0] == n
+    ha, hb = a.to_host(), b.to_host()
+    for k in ha.fields:
+        assert np.array_equal(getattr(ha, k), getattr(hb, k), equal_nan=True), k
