@@ -866,7 +866,7 @@ struct Side {
   int dev = -1;
   cudaStream_t st = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_join = nullptr;
-  cudaEvent_t ev_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_done = nullptr;  // the side work of this stream's last chunk has finished
   int ensure() {
     int d = 0;
     if (cudaGetDevice(&d) != cudaSuccess) return PP_E_CUDA;
@@ -876,8 +876,7 @@ struct Side {
         cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ev_done[0], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ev_done[1], cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming) != cudaSuccess) {
       cudaError_t e = cudaGetLastError();
       ppi::set_cuda_error("side stream", (int)e, cudaGetErrorString(e));
       release();
@@ -890,10 +889,8 @@ struct Side {
     if (ev_a) cudaEventDestroy(ev_a);
     if (ev_b) cudaEventDestroy(ev_b);
     if (ev_join) cudaEventDestroy(ev_join);
-    for (int i = 0; i < 2; i++) {
-      if (ev_done[i]) cudaEventDestroy(ev_done[i]);
-      ev_done[i] = nullptr;
-    }
+    if (ev_done) cudaEventDestroy(ev_done);
+    ev_done = nullptr;
     if (st) cudaStreamDestroy(st);
     ev_a = ev_b = ev_join = nullptr;
     st = nullptr;
@@ -1212,7 +1209,7 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     sc.slow_nb = n_base + 2 * ci + 1;
     sc.dbg = dbg ? n_base + 2 * n_chunks : nullptr;
     // the side stream may still be reading this pipe's scratch for its previous chunk
-    if (ci >= pipes) cudaStreamWaitEvent(ls, side.ev_done[0], 0);
+    if (ci >= pipes) cudaStreamWaitEvent(ls, side.ev_done, 0);
     pe = phase_begin();
     phase_mark(pe, 0, ls);
     k_prep<<<grid_for(cnt, 12), kBlock, smem, ls>>>(map->dev_table, map->n, *cfg, fin, sc, cnt);
@@ -1237,10 +1234,10 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     cudaStreamWaitEvent(side.st, side.ev_b, 0);
     k_slow<<<side_grid, kBlock, smem, side.st>>>(map->dev_table, map->n, *cfg, fin, fout, sc,
                                                  sc.slow_qb, sc.slow_nb);
-    cudaEventRecord(side.ev_done[0], side.st);
+    cudaEventRecord(side.ev_done, side.st);
     ppi::count_launch(mc > 0 ? 6 : 5);
     if (stats_dev) {  // this chunk's statistics, once its queued frames are planned too
-      cudaStreamWaitEvent(ls, side.ev_done[0], 0);
+      cudaStreamWaitEvent(ls, side.ev_done, 0);
       stats_kernel<<<stats_grid(cnt), 256, 0, ls>>>(fout, cnt, (unsigned long long *)stats_dev);
       ppi::count_launch();
     }
@@ -1249,7 +1246,7 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
   }
   // join: every pipe waits for its side stream's last kernels, the caller's stream for every pipe
   for (int k = 0; k < pipes && k < ci; k++) {
-    cudaStreamWaitEvent(lane_st[k], lane_side[k]->ev_done[0], 0);
+    cudaStreamWaitEvent(lane_st[k], lane_side[k]->ev_done, 0);
     if (pipes > 1) {
       cudaEventRecord(pp_.done[k], lane_st[k]);
       cudaStreamWaitEvent(st, pp_.done[k], 0);

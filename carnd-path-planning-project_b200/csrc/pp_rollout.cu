@@ -28,7 +28,7 @@ struct pp_rollouts {
   // per-tick frames and plans
   pp_frames fr;
   pp_plans pl;
-  int64_t *stats_tick, *stats_sum;  // stats_sum: running sum over all ticks (stats_tick: spare)
+  int64_t *stats_sum;  // running sum of the per-tick statistics over all ticks
   // Rollouts are independent, so they are cut into kGroups ranges that tick on their own
   // streams: one group's short kernels and side-stream tail overlap the other groups' work.
   static constexpr int kGroups = 4;
@@ -317,7 +317,7 @@ extern "C" int pp_rollouts_create(const pp_map *map, int64_t n, int32_t c, uint6
   const size_t p_i0 = take(N * 4), p_i1 = take(N * 4);
   const size_t p_cs = take(NC * 8), p_cd = take(NC * 8), p_cvs = take(NC * 8), p_cvd = take(NC * 8),
                p_cl = take(NC * 4), p_cw = take(NC * 4);
-  const size_t o_st = take(pp_rollouts::kGroups * PP_STATS_LEN * 8), o_ss = take(PP_STATS_LEN * 8);
+  const size_t o_ss = take(PP_STATS_LEN * 8);
   const size_t o_tk = take(N * 8);
   cudaError_t e = cudaMalloc((void **)&r->buf, off);
   if (e != cudaSuccess) {
@@ -378,7 +378,6 @@ extern "C" int pp_rollouts_create(const pp_map *map, int64_t n, int32_t c, uint6
   p.car_vd = (double *)(b + p_cvd);
   p.car_lane = (int32_t *)(b + p_cl);
   p.car_next_wp = (int32_t *)(b + p_cw);
-  r->stats_tick = (int64_t *)(b + o_st);
   r->stats_sum = (int64_t *)(b + o_ss);
   r->tick_dev = (int64_t *)(b + o_tk);
 
