@@ -670,7 +670,7 @@ k_emit(const __grid_constant__ pp_config cfg, const __grid_constant__ pp_plans o
     uint32_t flags = sc.e_flags[f];
     int bail;
     PointSink pts = make_sink<PointSink>(out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN);
-    const int np = traj_emit<true>(kn, cfg, ctl, cx, cy, ca, sa, sc.e_np[f], pts, flags, bail);
+    const int np = traj_emit_lean(kn, cfg, ctl, cx, cy, ca, sa, sc.e_np[f], pts, flags, bail);
     if (bail) {
       sc.slow_qb[atomicAdd(sc.slow_nb, 1)] = (int32_t)f;
       if (sc.dbg) atomicAdd(sc.dbg + bail, 1);
@@ -1263,9 +1263,9 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     }
     const int32_t *r = h.data() + 2 * n_chunks;
     std::fprintf(stderr,
-                 "pp_plan_batch: %lld frames, queued by k_decide %ld, by k_emit %ld (knots %d, "
-                 "atan2 %d, fmod %d, sincos %d)\n",
-                 (long long)n_frames, a, b, r[1], r[2], r[3], r[4]);
+                 "pp_plan_batch: %lld frames, queued by k_decide %ld, by k_emit %ld (knots not "
+                 "staged %d, operand outside the lean arithmetic %d)\n",
+                 (long long)n_frames, a, b, r[1], r[5]);
   }
   if (!caller_scratch) cudaFreeAsync(buf, st);
   if (rc == PP_OK) rc = check_launch("plan pipeline join");

@@ -213,8 +213,20 @@ __global__ void k_selftest_math(int64_t n, unsigned long long seed, unsigned lon
   unsigned long long st = mix64(seed ^ (unsigned long long)i * 0xD1B54A32D192ED03ull);
   // ordinary magnitudes most of the time, extreme ones sometimes (guards must route them)
   const bool wide = (i & 15) == 0;
-  const double a = rnd_double(st, wide ? -1000 : -40, wide ? 1000 : 40);
+  double a = rnd_double(st, wide ? -1000 : -40, wide ? 1000 : 40);
   const double b = rnd_double(st, wide ? -1000 : -40, wide ? 1000 : 40);
+  if ((i & 63) == 5) a = (i & 64) ? 0.0 : -0.0;  // signed zeros stay on the short path
+  if ((i & 3) == 2) {
+    // a numerator whose quotient by 50 lies next to a rounding boundary: 50 * (q + ulp/2),
+    // moved by up to two ulps either way (the one-correction x/50 has no slack to spare)
+    const double q = a;
+    const double u = fabs(__longlong_as_double(__double_as_longlong(q) + 1) - q);
+    const double hi = q * 50.0, lo = fma(q, 50.0, -hi);
+    double m = hi + (lo + (q < 0 ? -25.0 : 25.0) * u);
+    const int k = (int)((i >> 2) % 5) - 2;
+    m = __longlong_as_double(__double_as_longlong(m) + k);
+    a = m;
+  }
   const Rcp r = rcp_make(b);
   const double q = div_by(a, r), qe = a / b;
   if (__double_as_longlong(q) != __double_as_longlong(qe)) atomicAdd(&counts[0], 1ull);
