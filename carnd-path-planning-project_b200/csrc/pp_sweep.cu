@@ -176,7 +176,16 @@ k_sweep_emit(const __grid_constant__ pp_config cfg, const __grid_constant__ pp_f
   SharedKnots kn{s_knots, code & 0xff, (code >> 8) != 0};
   uint32_t flags = 0;
   int bail;
-  traj_emit<false>(kn, cfg, sc, s_head[3], s_head[4], s_head[5], s_head[6], np, so, flags, bail);
+  // the emission kernel's lean loop first; a candidate with an operand it does not cover
+  // (bail 5: e.g. a standstill's zero chord) is redone on the complete loop — same values
+  traj_emit_lean(kn, cfg, sc, s_head[3], s_head[4], s_head[5], s_head[6], np, so, flags, bail);
+  if (bail == 5) {
+    so.init();
+    for (int i = 0; i < np; i++)
+      so.put(i, in.prev_x[f * PP_PREV_KEEP + i], in.prev_y[f * PP_PREV_KEEP + i]);
+    flags = 0;
+    traj_emit<false>(kn, cfg, sc, s_head[3], s_head[4], s_head[5], s_head[6], np, so, flags, bail);
+  }
   *dst = bail ? PP_SWEEP_BAD : so.score(cfg, lane, target_lane[f]);
 }
 
