@@ -20,10 +20,13 @@ for f in os.listdir(tmp):
     if not f.endswith(".cubin"):
         continue
     txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
-    inside, cur = False, None
+    inside, cur, matched = False, None, False
     for ln in txt.splitlines():
         if ln.startswith(".text."):
-            inside = kern in ln
+            # the first matching section only: template instances (k_emit<PairOut>, <ArrayOut>)
+            # share a name and their offsets would overwrite each other
+            inside = (kern in ln) and not matched
+            matched = matched or inside
             cur = None
         if not inside:
             continue

@@ -261,3 +261,40 @@ def test_plan_stats_batch_equals_the_two_calls(pp, torch_cuda, gmap, n):
     ha, hb = a.to_host(), b.to_host()
     for k in ha.fields:
         assert np.array_equal(getattr(ha, k), getattr(hb, k), equal_nan=True), k
+
+
+def test_standstill_and_constant_speed_frames(pp, torch_cuda, gmap, oracle):
+    """Operands the emission kernel's lean arithmetic hands to the complete path or treats
+    specially: a car standing at keeping distance behind a stopped car (target speed 0 -> zero
+    arc step -> 0/0 chord ratio: the reference emits ONE NaN point and stops), and cruising
+    exactly at the target speed (zero numerators in the speed ramp).  Same bars as everywhere
+    else, NaN pattern included."""
+    cfg = pp.default_config()
+    fb = pp.synth_frames(gmap, 3000, 12, seed=77, rare_permille=0)
+    yaw = np.deg2rad(fb.ego_yaw_deg[:1000])
+    fb.ego_speed_mph[:1000] = 0.0
+    fb.prev_n[:1000] = 0
+    fb.n_cars[:1000] = 1  # one stopped car inside the keep-distance leeway (src/main.cpp:1130-1136)
+    fb.car_x[:1000, 0] = fb.ego_x[:1000] + 14.7 * np.cos(yaw)
+    fb.car_y[:1000, 0] = fb.ego_y[:1000] + 14.7 * np.sin(yaw)
+    fb.car_vx[:1000, 0] = 0.0
+    fb.car_vy[:1000, 0] = 0.0
+    fb.n_cars[1000:2000] = 0      # free road, no previous path, already at the speed limit
+    fb.prev_n[1000:2000] = 0
+    fb.ego_speed_mph[1000:2000] = cfg.max_speed / 0.44704
+    assert fb.ego_speed_mph[1000] * 0.44704 == cfg.max_speed
+    want = oracle.plan(fb, threads=8)
+    # the constructed cases do occur in the reference's own arithmetic
+    assert ((want.target_speed[:1000] == 0) & (want.n_points[:1000] == 1)).sum() > 800
+    assert np.isnan(want.next_x[:1000, 0]).sum() > 800
+    assert (want.target_speed[1000:2000] == cfg.max_speed).all()
+    got = gpu_plan(pp, torch_cuda, gmap, fb)
+    assert_plans_equal(plans_dict(got), plans_dict(want), ALL_FLAGS, bitwise_traj=False)
+    # fused single-kernel path: bitwise the same as the pipeline here as well
+    assert pp.lib.pp_set_kernel_variant(1) == 0
+    try:
+        fused = gpu_plan(pp, torch_cuda, gmap, fb)
+    finally:
+        pp.lib.pp_set_kernel_variant(0)
+    for k in ("next_x", "next_y", "n_points", "flags", "target_lane"):
+        assert np.array_equal(getattr(got, k), getattr(fused, k), equal_nan=True), k
