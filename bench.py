@@ -509,7 +509,7 @@ def main():
                          "algorithmic_bytes_per_frame": bytes_in + BYTES_OUT,
                          "algorithmic_bytes_per_step": alg_bytes,
                          "note": "FP64-issue / divergence bound, not HBM bound (DESIGN.md §2): "
-                                 "1,520 B against ~35 k FP64-heavy instructions per frame"},
+                                 "1,520 B against ~41 k instructions per frame, a third to a half of them FP64"},
             "clocks": clocks,
             "stats": {"frames": int(stats[0]), "points": int(stats[1]),
                       "lane_changes": int(stats[8])},
