@@ -460,25 +460,30 @@ k_cars(const double *__restrict__ map_table, int n_wp, const __grid_constant__ p
     hist[lane] = 0;
     __syncwarp();
     int key[kTileK];  // bin | rank within the bin << 8
+    // pass 1: the bins.  Every load is unconditional (slots past n_cars are allocated padding,
+    // a clamped index keeps the last tile in range) and independent of the others, so the
+    // loads of all eight items go out together; as `if (j < n_cars[f]) { load ... }` each item
+    // cost two dependent trips to memory.
 #pragma unroll
     for (int k = 0; k < kTileK; k++) {
       const int64_t t = base + k * 32 + lane;
-      int bin = kBins;
-      if (t < total) {
-        const unsigned xi = r0 + (unsigned)(k * 32 + lane);
-        const unsigned qi = __umulhi(xi, mc_magic);
-        const int64_t f = f0 + qi;
-        const int j = (int)(xi - qi * (unsigned)mc);
-        if (j < in.n_cars[f]) {
-          const float dx = (float)(in.car_x[t] - sc.x[f]), dy = (float)(in.car_y[t] - sc.y[f]);
-          const int wp = sc.wp[f];
-          const float len = (float)row(m, wp)[11];  // centre lane's segment length
-          const float q = sqrtf(dx * dx + dy * dy) / len;
-          bin = q < (float)(kBins - 1) ? (int)q : kBins - 1;  // NaN -> last bin
-        }
-      }
-      key[k] = bin | (atomicAdd(&hist[bin], 1) << 8);
+      const bool in_range = t < total;
+      const int64_t tc = in_range ? t : total - 1;
+      const unsigned xi = r0 + (unsigned)(tc - base);
+      const unsigned qi = __umulhi(xi, mc_magic);
+      const int64_t f = f0 + qi;
+      const int j = (int)(xi - qi * (unsigned)mc);
+      const int nc = in.n_cars[f];
+      const float dx = (float)(in.car_x[tc] - sc.x[f]), dy = (float)(in.car_y[tc] - sc.y[f]);
+      const int wp = sc.wp[f];
+      const float len = (float)row(m, wp)[11];  // centre lane's segment length
+      const float q = sqrtf(dx * dx + dy * dy) / len;
+      const int b = q < (float)(kBins - 1) ? (int)q : kBins - 1;  // NaN -> last bin
+      key[k] = (in_range & (j < nc)) ? b : kBins;
     }
+    // pass 2: rank within the bin
+#pragma unroll
+    for (int k = 0; k < kTileK; k++) key[k] |= atomicAdd(&hist[key[k]], 1) << 8;
     __syncwarp();
     // exclusive prefix over the bins (lane b owns bin b)
     const int cnt = hist[lane];
