@@ -29,6 +29,10 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+# before torch / CUDA start: the planner runs nine streams, the default is 8 hardware work
+# queues (pp_api.cu, INTEGRATION.md "Threading")
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import subprocess
 import sys
 import tempfile

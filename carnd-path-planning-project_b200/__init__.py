@@ -13,6 +13,10 @@ from __future__ import annotations
 import ctypes as C
 import os
 
+# more hardware work queues than the default 8 (see pp_api.cu: the planner uses nine streams);
+# read at CUDA context creation, so set it before anything touches the device
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 from . import abi

@@ -11,6 +11,17 @@
 
 #include "pp_internal.h"
 
+// The planner keeps up to nine streams busy at once (the caller's, four chunk pipes and their
+// side streams; a rollouts object: four groups and their side streams).  CUDA maps streams onto
+// CUDA_DEVICE_MAX_CONNECTIONS hardware work queues, 8 by default: with more streams than queues
+// two independent streams share one and serialise, differently from run to run (the closed-loop
+// rollout job measured anywhere between 62 and 217 M ego-frames/s; with 32 queues 200-207 M,
+// profiles/probe_connections.sh).  The variable is read when the CUDA context is created, so it
+// is set when this library is loaded — unless the process already chose a value.
+__attribute__((constructor)) static void pp_more_work_queues() {
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+}
+
 namespace {
 std::mutex g_err_mu;
 std::string g_err = "";

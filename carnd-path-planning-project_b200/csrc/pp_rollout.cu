@@ -474,7 +474,11 @@ extern "C" void pp_rollouts_destroy(pp_rollouts *r) {
 namespace {
 
 // One tick of every group: issued on the group streams, forked from / joined to `st`.
-int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStream_t st) {
+// One tick of every group.  Groups are independent (a rollout's tick t+1 depends on its own tick
+// t only), so a run forks the group streams off `st` once (`fork`) and joins them once (`join`);
+// a captured tick needs both so that the graph is closed.
+int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStream_t st,
+               bool fork = true, bool join = true) {
   // device rows of the padded table: logical row 0 starts PPD_PAD_ROWS rows in
   const Track trk{r->map->dev_table + (size_t)PPD_PAD_ROWS * PP_MAP_STRIDE, r->map->n, PP_MAP_STRIDE};
   // groups: contiguous ranges of rollouts (at least 4096 each, so that small jobs stay whole)
@@ -482,8 +486,10 @@ int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStre
   while (groups > 1 && r->n / groups < 4096) groups--;
   const int64_t per = (r->n + groups - 1) / groups;
   const int mc = r->fr.max_cars;
-  cudaEventRecord(r->fork, st);
-  for (int g = 0; g < groups; g++) cudaStreamWaitEvent(r->gs[g], r->fork, 0);
+  if (fork) {
+    cudaEventRecord(r->fork, st);
+    for (int g = 0; g < groups; g++) cudaStreamWaitEvent(r->gs[g], r->fork, 0);
+  }
   const int64_t launches0 = pp_launch_count();
   for (int g = 0; g < groups; g++) {
     const int64_t lo = g * per;
@@ -508,13 +514,22 @@ int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStre
     ppi::count_launch(2);
   }
   r->launches_per_tick = pp_launch_count() - launches0;
-  for (int g = 0; g < groups; g++) {  // join
-    cudaEventRecord(r->g_done[g], r->gs[g]);
-    cudaStreamWaitEvent(st, r->g_done[g], 0);
+  if (join) {
+    for (int g = 0; g < groups; g++) {
+      cudaEventRecord(r->g_done[g], r->gs[g]);
+      cudaStreamWaitEvent(st, r->g_done[g], 0);
+    }
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail("rollout tick", e);
   return PP_OK;
+}
+
+void issue_join_only(pp_rollouts *r, cudaStream_t st) {
+  for (int g = 0; g < pp_rollouts::kGroups; g++) {
+    cudaEventRecord(r->g_done[g], r->gs[g]);
+    cudaStreamWaitEvent(st, r->g_done[g], 0);
+  }
 }
 
 bool same_cfg(const pp_config &a, const pp_config &b) { return std::memcmp(&a, &b, sizeof a) == 0; }
@@ -527,11 +542,12 @@ extern "C" int pp_rollouts_run(pp_rollouts *r, const pp_config *cfg, int64_t n_t
     return PP_E_ARG;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   if (n_ticks == 0) return PP_OK;
-  // A tick is ~50 short launches over 8 streams (4 groups, each with its side stream).  It can
+  // A tick is ~36 short launches over 8 streams (4 groups, each with its side stream).  It can
   // be captured once and replayed as a CUDA graph (PP_ROLLOUT_GRAPH=1; the pipeline's scratch is
-  // owned by the rollouts object, so the graph holds only kernels, memsets and event edges), but
-  // replay measured erratic (67-138 M ego-frames/s run to run on one B200) where direct issue
-  // gives 123-144 M, so direct issue is the default.
+  // owned by the rollouts object, so the graph holds only kernels, memsets and event edges).
+  // With enough hardware work queues (pp_api.cu) both ways run at the same, stable speed
+  // (≈ 200 M ego-frames/s for 65,536 rollouts on one B200); direct issue is the default because
+  // it needs no per-tick join of the groups.
   const bool use_graph = n_ticks >= 8 && getenv("PP_ROLLOUT_GRAPH") != nullptr;
   if (use_graph) {
     cudaStream_t caller = st;
@@ -577,8 +593,11 @@ extern "C" int pp_rollouts_run(pp_rollouts *r, const pp_config *cfg, int64_t n_t
     return PP_OK;
   }
   for (int64_t t = 0; t < n_ticks; t++) {
-    const int rc = issue_tick(r, cfg, consume_k, st);
-    if (rc != PP_OK) return rc;
+    const int rc = issue_tick(r, cfg, consume_k, st, t == 0, t == n_ticks - 1);
+    if (rc != PP_OK) {
+      if (t > 0) issue_join_only(r, st);  // keep `st` ordered after what was already issued
+      return rc;
+    }
     r->tick++;
   }
   return PP_OK;
