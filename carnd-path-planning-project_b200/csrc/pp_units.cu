@@ -247,6 +247,25 @@ __global__ void k_selftest_math(int64_t n, unsigned long long seed, unsigned lon
   if (d < 0) d = -d;
   if ((t1 < 0) != (t2 < 0) && t1 != t2) d = 1000;  // different signs: flag loudly
   atomicMax(&counts[3], (unsigned long long)d);
+  // ---- the emission kernel's lean versions against the guarded helpers, inside the ranges
+  // their flag leaves clear (outside, the frame goes to the complete path anyway)
+  {
+    const Rcp g = rcp_make(b), l = rcp_lean(b);
+    if (g.ok != l.ok || (g.ok && __double_as_longlong(g.y) != __double_as_longlong(l.y)))
+      atomicAdd(&counts[4], 1ull);
+    if (mag_ok(a)) {
+      const double q = div50_raw(a), qe = a / 50.0;
+      // a -0 numerator comes back as +0 (documented): compare values, not zero signs
+      if (!(q == qe) || (qe != 0 && __double_as_longlong(q) != __double_as_longlong(qe)))
+        atomicAdd(&counts[5], 1ull);
+    }
+    const double l1 = atan2_lean(dy, dx);
+    if (__double_as_longlong(l1) != __double_as_longlong(t1)) atomicAdd(&counts[6], 1ull);
+    st = mix64(st);
+    const double xw = 25.132741228718345 * ((double)(st >> 11) * (1.0 / 9007199254740992.0));  // [0, 8 pi)
+    const double w1 = wrap_lean(xw), w2 = fmod(xw, m);
+    if (__double_as_longlong(w1) != __double_as_longlong(w2)) atomicAdd(&counts[7], 1ull);
+  }
 }
 
 __global__ void k_project_speed(const double *table, int n_wp, const double *vx, const double *vy,
@@ -459,7 +478,7 @@ int pp_speed_controller_batch(int32_t op, const double *start, double *target, d
 
 int pp_selftest_math(int64_t n, uint64_t seed, int64_t *counts_dev, void *stream) {
   if (!counts_dev || n < 0) return PP_E_ARG;
-  if (cudaMemsetAsync(counts_dev, 0, 4 * sizeof(int64_t), (cudaStream_t)stream) != cudaSuccess)
+  if (cudaMemsetAsync(counts_dev, 0, 8 * sizeof(int64_t), (cudaStream_t)stream) != cudaSuccess)
     return finish("pp_selftest_math memset");
   if (n == 0) return PP_OK;
   k_selftest_math<<<grid_for(n), kB, 0, (cudaStream_t)stream>>>(

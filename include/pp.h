@@ -341,9 +341,12 @@ int pp_dev_sync(void);
 
 /* Device self-test of the exact-arithmetic helpers the kernels use in place of
  * generic divisions / fmod / atan2 (Markstein quotient with cached reciprocal,
- * x/50, angle wrap, small-slope atan): n random trials; counts_dev[0..2] =
- * number of results that differ bitwise from the generic operation (must be 0),
- * counts_dev[3] = largest |fast atan - atan2| seen, in ulps. */
+ * x/50, angle wrap, small-slope atan): n random trials; counts_dev[8]:
+ * [0..2] = number of results that differ bitwise from the generic operation
+ * (must be 0), [3] = largest |fast atan - atan2| seen, in ulps, [4..7] = number
+ * of results of the emission kernel's unguarded versions (reciprocal, x/50,
+ * atan, angle wrap) that differ from the guarded helpers inside the range their
+ * "not covered" flag leaves clear (must be 0). */
 int pp_selftest_math(int64_t n, uint64_t seed, int64_t *counts_dev, void *cuda_stream);
 
 /* ---- synthetic workload (host).  Counter-based RNG

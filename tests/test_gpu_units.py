@@ -205,8 +205,11 @@ def test_exact_arithmetic_helpers_selftest(pp, T):
     random trials incl. extreme magnitudes — and the forward-step atan (slopes up
     to +-3, i.e. all three rotation classes and the library fall-through) must stay
     within 6 ulp of the library atan2 (< 7e-16 rad; trajectory tolerance 1e-9)."""
-    counts = T.zeros(4, dtype=T.int64, device="cuda")
+    counts = T.zeros(8, dtype=T.int64, device="cuda")
     assert pp.lib.pp_selftest_math(C.c_int64(1 << 27), C.c_uint64(12345), p(counts), None) == 0
     c = counts.cpu().numpy()
     assert c[0] == 0 and c[1] == 0 and c[2] == 0, c
     assert 0 <= c[3] <= 6, c
+    # the emission kernel's unguarded versions (reciprocal without range checks, one-correction
+    # x/50, atan and angle wrap without fall-backs) equal the guarded helpers bit for bit
+    assert (c[4:8] == 0).all(), c
