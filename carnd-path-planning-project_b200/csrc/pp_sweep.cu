@@ -184,7 +184,7 @@ k_sweep_emit(const __grid_constant__ pp_config cfg, const __grid_constant__ pp_f
     for (int i = 0; i < np; i++)
       so.put(i, in.prev_x[f * PP_PREV_KEEP + i], in.prev_y[f * PP_PREV_KEEP + i]);
     flags = 0;
-    traj_emit<false>(kn, cfg, sc, s_head[3], s_head[4], s_head[5], s_head[6], np, so, flags, bail);
+    traj_emit(kn, cfg, sc, s_head[3], s_head[4], s_head[5], s_head[6], np, so, flags, bail);
   }
   *dst = bail ? PP_SWEEP_BAD : so.score(cfg, lane, target_lane[f]);
 }
@@ -242,7 +242,7 @@ k_sweep_select(const __grid_constant__ pp_config cfg, const __grid_constant__ pp
     ArrayOut pts{ox, oy};
     uint32_t flags = 0;
     int bail;
-    np = traj_emit<false>(kn, cfg, sc, sw.est[3 * sw.n3 + q], sw.est[4 * sw.n3 + q],
+    np = traj_emit(kn, cfg, sc, sw.est[3 * sw.n3 + q], sw.est[4 * sw.n3 + q],
                           sw.est[5 * sw.n3 + q], sw.est[6 * sw.n3 + q], np, pts, flags, bail);
   }
   for (int i = np; i < PP_PATH_LEN; i++) {
