@@ -276,6 +276,13 @@ class ClockSampler:
             if self.h is None:
                 self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            # first NVML queries can take > 100 ms (longer than the whole timed region): pay for
+            # them here, not on the sampling thread
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons"):
+                pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            else:
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
             self.ok = True
         except Exception:
             self.ok = False
