@@ -298,3 +298,40 @@ def test_standstill_and_constant_speed_frames(pp, torch_cuda, gmap, oracle):
         pp.lib.pp_set_kernel_variant(0)
     for k in ("next_x", "next_y", "n_points", "flags", "target_lane"):
         assert np.array_equal(getattr(got, k), getattr(fused, k), equal_nan=True), k
+
+
+def test_scattered_ego_positions(pp, torch_cuda, gmap, oracle):
+    """Closest-waypoint search and everything behind it for ego positions that the synthetic
+    generator never produces: scattered kilometres beyond the track, exactly on waypoints and
+    midway between two (ties in distance).  Pipeline against the oracle and against the fused
+    kernel, bit for bit.  (Non-finite positions are left out: the reference's own segment walk
+    does not terminate on them, src/main.cpp:214-274.)"""
+    rng = np.random.default_rng(5)
+    n = 60000
+    fb = pp.synth_frames(gmap, n, 4, seed=91, rare_permille=0)
+    fb.prev_n[:] = 0  # the ego position is the telemetry position
+    tab = gmap.table()  # columns 0, 1: the waypoints
+    wx, wy = tab[:, 0].copy(), tab[:, 1].copy()
+    k = n // 6
+    fb.ego_x[:k] = rng.uniform(wx.min() - 3000, wx.max() + 3000, k)       # anywhere, mostly far
+    fb.ego_y[:k] = rng.uniform(wy.min() - 3000, wy.max() + 3000, k)
+    i = rng.integers(0, len(wx), k)
+    fb.ego_x[k:2 * k], fb.ego_y[k:2 * k] = wx[i], wy[i]                   # on a waypoint
+    j = (i + 1) % len(wx)
+    fb.ego_x[2 * k:3 * k] = (wx[i] + wx[j]) / 2                             # midway: near-ties
+    fb.ego_y[2 * k:3 * k] = (wy[i] + wy[j]) / 2
+    want = oracle.plan(fb, threads=8)
+    got = gpu_plan(pp, torch_cuda, gmap, fb)
+    assert np.array_equal(got.ref_wp, want.ref_wp), np.argwhere(got.ref_wp != want.ref_wp)[:5]
+    assert np.array_equal(got.ego_lane, want.ego_lane) and np.array_equal(got.target_lane, want.target_lane)
+    on_track = slice(k, 3 * k)  # full bars where the plan is well conditioned
+    assert_plans_equal({a: v[on_track] for a, v in plans_dict(got).items()},
+                       {a: v[on_track] for a, v in plans_dict(want).items()}, ALL_FLAGS,
+                       bitwise_traj=False)
+    try:
+        pp.set_kernel_variant(1)
+        fused = gpu_plan(pp, torch_cuda, gmap, fb)
+    finally:
+        pp.set_kernel_variant(0)
+    for name in got.fields:
+        assert np.array_equal(getattr(got, name), getattr(fused, name), equal_nan=True), name
