@@ -259,6 +259,14 @@ static vec2 lane_pos(const ppo_map *m, const refstate *rs, double s, int lane, i
     nxt = wp_center(m, wp, lane);
     prv = wp_center(m, wp - 1, lane);
     double wl = len2(nxt.x - prv.x, nxt.y - prv.y);
+    /* NOT in the reference: with a NaN or infinite s (a NaN pose) neither branch below ever
+     * breaks and the reference spins forever.  Both this restatement and the CUDA path leave the
+     * loop with dest = s, so a poisoned frame yields NaN points instead of a hang. */
+    if (!(fabs(s) <= 1e300)) {
+      dest = s;
+      *out_dist = s;
+      break;
+    }
     if (s > 0) {
       double rem = wl * (1 - ratio);
       if (s <= rem) {

@@ -304,8 +304,7 @@ def test_scattered_ego_positions(pp, torch_cuda, gmap, oracle):
     """Closest-waypoint search and everything behind it for ego positions that the synthetic
     generator never produces: scattered kilometres beyond the track, exactly on waypoints and
     midway between two (ties in distance).  Pipeline against the oracle and against the fused
-    kernel, bit for bit.  (Non-finite positions are left out: the reference's own segment walk
-    does not terminate on them, src/main.cpp:214-274.)"""
+    kernel, bit for bit; plus non-finite poses, which must not hang anything."""
     rng = np.random.default_rng(5)
     n = 60000
     fb = pp.synth_frames(gmap, n, 4, seed=91, rare_permille=0)
@@ -320,10 +319,17 @@ def test_scattered_ego_positions(pp, torch_cuda, gmap, oracle):
     j = (i + 1) % len(wx)
     fb.ego_x[2 * k:3 * k] = (wx[i] + wx[j]) / 2                             # midway: near-ties
     fb.ego_y[2 * k:3 * k] = (wy[i] + wy[j]) / 2
+    # poisoned poses: the reference never returns from get_lane_pos for a NaN pose
+    # (src/main.cpp:282-325); this implementation and its oracle leave that loop, so the frame
+    # costs nothing worse than NaN points — above all the kernel must come back
+    bad = slice(3 * k, 3 * k + 6)
+    fb.ego_x[bad] = [np.nan, 0.0, np.nan, np.inf, -np.inf, 1e200]
+    fb.ego_y[bad] = [0.0, np.nan, np.nan, 0.0, np.inf, 1e200]
     want = oracle.plan(fb, threads=8)
     got = gpu_plan(pp, torch_cuda, gmap, fb)
     assert np.array_equal(got.ref_wp, want.ref_wp), np.argwhere(got.ref_wp != want.ref_wp)[:5]
     assert np.array_equal(got.ego_lane, want.ego_lane) and np.array_equal(got.target_lane, want.target_lane)
+    assert np.array_equal(got.n_points, want.n_points)
     on_track = slice(k, 3 * k)  # full bars where the plan is well conditioned
     assert_plans_equal({a: v[on_track] for a, v in plans_dict(got).items()},
                        {a: v[on_track] for a, v in plans_dict(want).items()}, ALL_FLAGS,
