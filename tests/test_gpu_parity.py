@@ -341,3 +341,32 @@ def test_scattered_ego_positions(pp, torch_cuda, gmap, oracle):
         pp.set_kernel_variant(0)
     for name in got.fields:
         assert np.array_equal(getattr(got, name), getattr(fused, name), equal_nan=True), name
+
+
+def test_poisoned_fields_terminate_and_match(pp, torch_cuda, gmap, oracle):
+    """NaN / infinite / huge / denormal values in every input field (car position and velocity,
+    yaw, speed, previous path): the kernels return and every integer output, NaN pattern included,
+    equals the oracle's — the select-based forms must treat NaN like the reference's branches."""
+    n = 6400
+    fb = pp.synth_frames(gmap, n, 4, seed=92, rare_permille=0)
+    vals = [np.nan, np.inf, -np.inf, 1e200, 1e-310]
+    fields = ["car_x", "car_y", "car_vx", "car_vy", "ego_yaw_deg", "ego_speed_mph", "prev_x", "prev_y"]
+    for f in range(n):
+        a = getattr(fb, fields[(f // 5) % 8])
+        if a.ndim == 2:
+            a[f, (f // 40) % a.shape[1]] = vals[f % 5]
+        else:
+            a[f] = vals[f % 5]
+    want = oracle.plan(fb, threads=8)
+    got = gpu_plan(pp, torch_cuda, gmap, fb)
+    for name in ("ref_wp", "ego_lane", "target_lane", "n_points", "car_lane"):
+        bad = np.argwhere(getattr(got, name) != getattr(want, name))
+        assert len(bad) == 0, (name, bad[:5].tolist())
+    assert np.array_equal(np.isnan(got.next_x), np.isnan(want.next_x))
+    try:
+        pp.set_kernel_variant(1)
+        fused = gpu_plan(pp, torch_cuda, gmap, fb)
+    finally:
+        pp.set_kernel_variant(0)
+    for name in ("next_x", "next_y", "n_points", "flags", "target_lane"):
+        assert np.array_equal(getattr(got, name), getattr(fused, name), equal_nan=True), name
