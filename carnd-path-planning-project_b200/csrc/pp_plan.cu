@@ -71,6 +71,32 @@ struct FrameCtx {
   uint32_t flags;
 };
 
+// One point's term of the statistics' trajectory checksum (PP_STAT_XSUM, definition in
+// include/pp.h): fixed point, 1/256 m, finite coordinates only.  Integer sums: order-free.
+PPD_INLINE long long fx_point(double x, double y) {
+  if (x == x && y == y && fabs(x) < 1e12 && fabs(y) < 1e12)
+    return (long long)(x * 256.0) + (long long)(y * 256.0);
+  return 0;
+}
+// add a thread's partial checksum to the global one: one atomic per warp (every lane calls)
+PPD_INLINE void xsum_commit(unsigned long long *xsum, long long v) {
+  unsigned long long u = (unsigned long long)v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) u += __shfl_down_sync(0xffffffffu, u, o);
+  if ((threadIdx.x & 31) == 0 && u) atomicAdd(xsum, u);
+}
+// a point sink that also accumulates the checksum of what passes through it
+template <class Base>
+struct SumOut {
+  Base b;
+  long long acc;
+  PPD_INLINE void put(int i, double x, double y) {
+    b.put(i, x, y);
+    acc += fx_point(x, y);
+  }
+  PPD_INLINE void flush() { b.flush(); }
+};
+
 PPD_INLINE double ctx_dt0(const FrameCtx &c) { return c.nprev ? PP_PREV_KEEP / 50.0 : 0.0; }
 
 PPD_INLINE FrameCtx stage_prep(const MapView &m, const pp_config &cfg, const pp_frames &in,
@@ -344,6 +370,10 @@ struct Scratch {
   int32_t *slow_qa, *slow_qb;
   int32_t *slow_na, *slow_nb;
   int32_t *dbg;  // PP_DEBUG_SLOW: bail-out reasons of k_emit, else nullptr
+  // pp_plan_stats_batch: the trajectory checksum is accumulated where the points are produced
+  // (kept points in k_decide, new points in k_emit / k_fallback / k_slow) instead of re-reading
+  // 800 B per frame afterwards; nullptr otherwise
+  unsigned long long *xsum;
   int64_t n;  // frames in this chunk (stride of ratio)
 };
 constexpr int kEstHead = 7;  // sc.start, sc.target, sc.time, cx, cy, ca, sa
@@ -389,6 +419,7 @@ Scratch carve_scratch(char *base, int64_t n, int mc) {
   s.e_nk = (int32_t *)take(N * 4);
   s.e_flags = (uint32_t *)take(N * 4);
   s.slow_qa = s.slow_qb = s.slow_na = s.slow_nb = s.dbg = nullptr;  // set per chunk by the caller
+  s.xsum = nullptr;
   s.n = n;
   return s;
 }
@@ -589,6 +620,7 @@ k_decide(const double *__restrict__ map_table, int n_wp, const __grid_constant__
   m.n = n_wp;
   m.pad_lo = n_wp < PPD_PAD ? n_wp : PPD_PAD;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  long long xacc = 0;  // checksum of the kept points (= the stored previous points, :578)
   for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += stride) {
     FrameCtx c;
     load_ctx(sc, f, c);
@@ -598,6 +630,10 @@ k_decide(const double *__restrict__ map_table, int n_wp, const __grid_constant__
     reduce_cars(cfg, in, sc, f, c, tl_in, b, flags);
     const Decision d = stage_decide(cfg, in, out, f, c, b, tl_in, flags);
     flags = d.flags;
+    if (sc.xsum) {
+      for (int i = 0; i < c.nprev; i++)
+        xacc += fx_point(in.prev_x[f * PP_PREV_KEEP + i], in.prev_y[f * PP_PREV_KEEP + i]);
+    }
     double *e = sc.est + f;
     KnotSweep sw;
     sw.init(s_rows + threadIdx.x, blockDim.x, e, sc.n, kEstHead);
@@ -629,6 +665,7 @@ k_decide(const double *__restrict__ map_table, int n_wp, const __grid_constant__
     sc.e_nk[f] = cnt | (r0 > 0 ? kEstPartial : 0);
     sc.e_flags[f] = flags;
   }
+  if (sc.xsum) xsum_commit(sc.xsum, xacc);
 }
 
 template <class S>
@@ -649,12 +686,15 @@ PPD_INLINE PairOut make_sink<PairOut>(double *x, double *y) {
 #ifndef PP_EMIT_MINB
 #define PP_EMIT_MINB 4
 #endif
-template <class PointSink>  // PairOut when next_x / next_y are 16-byte aligned, else ArrayOut
+// PointSink: PairOut when next_x / next_y are 16-byte aligned, else ArrayOut; kSum: also
+// accumulate the statistics' checksum (sc.xsum)
+template <class PointSink, bool kSum>
 __global__ void __launch_bounds__(kBlock, PP_EMIT_MINB)
 k_emit(const __grid_constant__ pp_config cfg, const __grid_constant__ pp_plans out,
        const __grid_constant__ Scratch sc, int64_t n) {
   extern __shared__ double s_knots[];  // [5 * PPD_TAILK][blockDim.x]
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  long long xacc = 0;  // checksum of the points emitted here (frames that bail out add nothing)
   for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += stride) {
     const int code = sc.e_nk[f];
     if (code & kEstFallback) continue;  // queued for k_fallback
@@ -684,8 +724,16 @@ k_emit(const __grid_constant__ pp_config cfg, const __grid_constant__ pp_plans o
     kn.part = (code & kEstPartial) != 0;
     uint32_t flags = sc.e_flags[f];
     int bail;
-    PointSink pts = make_sink<PointSink>(out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN);
-    const int np = traj_emit_lean(kn, cfg, ctl, cx, cy, ca, sa, sc.e_np[f], pts, flags, bail);
+    int np;
+    if (kSum) {
+      SumOut<PointSink> pts{make_sink<PointSink>(out.next_x + f * PP_PATH_LEN,
+                                                 out.next_y + f * PP_PATH_LEN), 0};
+      np = traj_emit_lean(kn, cfg, ctl, cx, cy, ca, sa, sc.e_np[f], pts, flags, bail);
+      if (!bail) xacc += pts.acc;
+    } else {
+      PointSink pts = make_sink<PointSink>(out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN);
+      np = traj_emit_lean(kn, cfg, ctl, cx, cy, ca, sa, sc.e_np[f], pts, flags, bail);
+    }
     if (bail) {
       sc.slow_qb[atomicAdd(sc.slow_nb, 1)] = (int32_t)f;
       if (sc.dbg) atomicAdd(sc.dbg + bail, 1);
@@ -693,6 +741,7 @@ k_emit(const __grid_constant__ pp_config cfg, const __grid_constant__ pp_plans o
     }
     store_path_tail(out, f, np, flags);
   }
+  if (kSum) xsum_commit(sc.xsum, xacc);
 }
 
 // The angle-based generator (:848-901) for the frames k_decide queued.  Every
@@ -702,6 +751,7 @@ k_fallback(const __grid_constant__ pp_plans out, const __grid_constant__ Scratch
            const int32_t *__restrict__ queue, const int32_t *__restrict__ queue_n) {
   const int count = *queue_n;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  long long xacc = 0;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < count; q += stride) {
     const int64_t f = queue[q];
     const double *e = sc.est + f;
@@ -724,7 +774,11 @@ k_fallback(const __grid_constant__ pp_plans out, const __grid_constant__ Scratch
     tf.ncp = sc.e_nk[f] & 0xff;
     const int np = traj_fallback(tf, ctl, out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN);
     store_path_tail(out, f, np, sc.e_flags[f]);
+    if (sc.xsum)  // the new points (the kept ones were counted by k_decide)
+      for (int i = tf.np; i < np; i++)
+        xacc += fx_point(out.next_x[f * PP_PATH_LEN + i], out.next_y[f * PP_PATH_LEN + i]);
   }
+  if (sc.xsum) xsum_commit(sc.xsum, xacc);
 }
 
 // The complete path for the frames k_emit gave up on (a few hundred per
@@ -755,6 +809,13 @@ k_slow(const double *__restrict__ map_table, int n_wp, const __grid_constant__ p
     Behav b;
     reduce_cars(cfg, in, sc, f, c, tl_in, b, flags);
     stage_finish(m, cfg, in, out, f, c, b, tl_in, flags);
+    if (sc.xsum) {  // new points of the re-planned frame (rare: one atomic per frame is fine)
+      long long xacc = 0;
+      const int np = out.n_points[f];
+      for (int i = c.nprev; i < np; i++)
+        xacc += fx_point(out.next_x[f * PP_PATH_LEN + i], out.next_y[f * PP_PATH_LEN + i]);
+      if (xacc) atomicAdd(sc.xsum, (unsigned long long)xacc);
+    }
   }
 }
 
@@ -769,7 +830,8 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
   return v;
 }
 __global__ void __launch_bounds__(256)
-stats_kernel(const __grid_constant__ pp_plans p, int64_t n, unsigned long long *stats) {
+stats_kernel(const __grid_constant__ pp_plans p, int64_t n, unsigned long long *stats,
+             bool with_points) {
   __shared__ unsigned long long s_acc[PP_STATS_LEN];
   for (int i = threadIdx.x; i < PP_STATS_LEN; i += blockDim.x) s_acc[i] = 0;
   __syncthreads();
@@ -783,10 +845,11 @@ stats_kernel(const __grid_constant__ pp_plans p, int64_t n, unsigned long long *
   const bool wide = (((uintptr_t)p.next_x | (uintptr_t)p.next_y) & 15) == 0;
   constexpr int kU = 4;
   auto add_point = [&](double x, double y, bool live) {
-    if (live && x == x && y == y && fabs(x) < 1e12 && fabs(y) < 1e12)
-      xs += (long long)(x * 256.0) + (long long)(y * 256.0);
+    if (live) xs += fx_point(x, y);
   };
-  if (wide) {  // two points per load: a row holds an even number of points
+  if (!with_points) {
+    // the pipeline accumulated the checksum while it produced the points
+  } else if (wide) {  // two points per load: a row holds an even number of points
     const int64_t total = n * (PP_PATH_LEN / 2);
     const double2 *px = reinterpret_cast<const double2 *>(p.next_x);
     const double2 *py = reinterpret_cast<const double2 *>(p.next_y);
@@ -1136,8 +1199,10 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
   if ((rc = ensure_smem(k_decide, smem_decide)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_slow, smem)) != PP_OK) return rc;
   const size_t smem_emit = (size_t)5 * PPD_TAILK * kBlock * sizeof(double);
-  if ((rc = ensure_smem(k_emit<ArrayOut>, smem_emit)) != PP_OK) return rc;
-  if ((rc = ensure_smem(k_emit<PairOut>, smem_emit)) != PP_OK) return rc;
+  if ((rc = ensure_smem(k_emit<ArrayOut, false>, smem_emit)) != PP_OK) return rc;
+  if ((rc = ensure_smem(k_emit<PairOut, false>, smem_emit)) != PP_OK) return rc;
+  if ((rc = ensure_smem(k_emit<ArrayOut, true>, smem_emit)) != PP_OK) return rc;
+  if ((rc = ensure_smem(k_emit<PairOut, true>, smem_emit)) != PP_OK) return rc;
   const bool paired = (((uintptr_t)out->next_x | (uintptr_t)out->next_y) & 15) == 0;
 
   const bool fused = g_variant == 1 || (g_variant == 0 && n_frames < kFusedBelow);
@@ -1147,7 +1212,7 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     ppi::count_launch();
     if (stats_dev) {
       stats_kernel<<<stats_grid(n_frames), 256, 0, st>>>(*out, n_frames,
-                                                         (unsigned long long *)stats_dev);
+                                                         (unsigned long long *)stats_dev, true);
       ppi::count_launch();
     }
     return check_launch("plan_fused");
@@ -1223,6 +1288,7 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     sc.slow_na = n_base + 2 * ci;
     sc.slow_nb = n_base + 2 * ci + 1;
     sc.dbg = dbg ? n_base + 2 * n_chunks : nullptr;
+    sc.xsum = stats_dev ? (unsigned long long *)stats_dev + PP_STAT_XSUM : nullptr;
     // the side stream may still be reading this pipe's scratch for its previous chunk
     if (ci >= pipes) cudaStreamWaitEvent(ls, side.ev_done, 0);
     pe = phase_begin();
@@ -1240,10 +1306,18 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     cudaEventRecord(side.ev_a, ls);
     cudaStreamWaitEvent(side.st, side.ev_a, 0);
     k_fallback<<<side_grid, kBlock, 0, side.st>>>(fout, sc, sc.slow_qa, sc.slow_na);
-    if (paired)  // (a row is 400 bytes: every frame of an aligned array is aligned)
-      k_emit<PairOut><<<grid_for(cnt, 12), kBlock, smem_emit, ls>>>(*cfg, fout, sc, cnt);
-    else
-      k_emit<ArrayOut><<<grid_for(cnt, 12), kBlock, smem_emit, ls>>>(*cfg, fout, sc, cnt);
+    const int eg = grid_for(cnt, 12);
+    if (paired) {  // (a row is 400 bytes: every frame of an aligned array is aligned)
+      if (sc.xsum)
+        k_emit<PairOut, true><<<eg, kBlock, smem_emit, ls>>>(*cfg, fout, sc, cnt);
+      else
+        k_emit<PairOut, false><<<eg, kBlock, smem_emit, ls>>>(*cfg, fout, sc, cnt);
+    } else {
+      if (sc.xsum)
+        k_emit<ArrayOut, true><<<eg, kBlock, smem_emit, ls>>>(*cfg, fout, sc, cnt);
+      else
+        k_emit<ArrayOut, false><<<eg, kBlock, smem_emit, ls>>>(*cfg, fout, sc, cnt);
+    }
     phase_mark(pe, 4, ls);
     cudaEventRecord(side.ev_b, ls);
     cudaStreamWaitEvent(side.st, side.ev_b, 0);
@@ -1253,7 +1327,9 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     ppi::count_launch(mc > 0 ? 6 : 5);
     if (stats_dev) {  // this chunk's statistics, once its queued frames are planned too
       cudaStreamWaitEvent(ls, side.ev_done, 0);
-      stats_kernel<<<stats_grid(cnt), 256, 0, ls>>>(fout, cnt, (unsigned long long *)stats_dev);
+      // (per-frame counters only: the checksum was accumulated by the kernels above, sc.xsum)
+      stats_kernel<<<stats_grid(cnt), 256, 0, ls>>>(fout, cnt, (unsigned long long *)stats_dev,
+                                                    false);
       ppi::count_launch();
     }
     rc = check_launch("plan pipeline");
@@ -1328,7 +1404,8 @@ extern "C" int pp_stats_batch(const pp_plans *p, int64_t n_frames, int64_t *stat
   if (cudaMemsetAsync(stats_dev, 0, PP_STATS_LEN * sizeof(int64_t), st) != cudaSuccess)
     return check_launch("pp_stats_batch memset");
   if (n_frames == 0) return PP_OK;
-  stats_kernel<<<stats_grid(n_frames), 256, 0, st>>>(*p, n_frames, (unsigned long long *)stats_dev);
+  stats_kernel<<<stats_grid(n_frames), 256, 0, st>>>(*p, n_frames, (unsigned long long *)stats_dev,
+                                                     true);
   ppi::count_launch();
   return check_launch("stats_kernel");
 }
