@@ -260,9 +260,11 @@ static vec2 lane_pos(const ppo_map *m, const refstate *rs, double s, int lane, i
     prv = wp_center(m, wp - 1, lane);
     double wl = len2(nxt.x - prv.x, nxt.y - prv.y);
     /* NOT in the reference: with a NaN or infinite s (a NaN pose) neither branch below ever
-     * breaks and the reference spins forever.  Both this restatement and the CUDA path leave the
-     * loop with dest = s, so a poisoned frame yields NaN points instead of a hang. */
-    if (!(fabs(s) <= 1e300)) {
+     * breaks and the reference spins forever; with a huge finite s (a telemetry speed of 1e200)
+     * subtracting a segment length no longer changes s, or takes 1e15 steps.  Both this
+     * restatement and the CUDA path leave the loop with dest = s when |s| exceeds 10,000 km, so a
+     * poisoned frame yields garbage points instead of a hang. */
+    if (!(fabs(s) <= 1e7)) {
       dest = s;
       *out_dist = s;
       break;

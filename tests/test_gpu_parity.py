@@ -357,6 +357,8 @@ def test_poisoned_fields_terminate_and_match(pp, torch_cuda, gmap, oracle):
             a[f, (f // 40) % a.shape[1]] = vals[f % 5]
         else:
             a[f] = vals[f % 5]
+    fb.prev_n[::3] = 0  # cold starts take the telemetry speed: 1e200 mph makes get_lane_pos's s
+    #                     so large that subtracting a segment no longer changes it
     want = oracle.plan(fb, threads=8)
     got = gpu_plan(pp, torch_cuda, gmap, fb)
     for name in ("ref_wp", "ego_lane", "target_lane", "n_points", "car_lane"):
@@ -370,3 +372,37 @@ def test_poisoned_fields_terminate_and_match(pp, torch_cuda, gmap, oracle):
         pp.set_kernel_variant(0)
     for name in ("next_x", "next_y", "n_points", "flags", "target_lane"):
         assert np.array_equal(getattr(got, name), getattr(fused, name), equal_nan=True), name
+
+
+def test_plan_stats_batch_on_rare_and_poisoned_frames(pp, torch_cuda, gmap):
+    """The fused statistics (checksum accumulated inside the planning kernels) against the
+    stand-alone pass when many frames take the side paths — fallback generator, frames the
+    emission kernel hands back, standstills with one NaN point, poisoned inputs — and more than
+    one chunk is in flight."""
+    n = 280000
+    fb = pp.synth_frames(gmap, n, 6, seed=131, rare_permille=400)
+    vals = [np.nan, np.inf, -np.inf, 1e200, 1e-310]
+    fields = ["car_x", "car_y", "car_vx", "car_vy", "ego_yaw_deg", "ego_speed_mph", "prev_x", "prev_y"]
+    for f in range(0, n, 97):
+        a = getattr(fb, fields[(f // 5) % 8])
+        if a.ndim == 2:
+            a[f, (f // 40) % a.shape[1]] = vals[f % 5]
+        else:
+            a[f] = vals[f % 5]
+    yaw = np.deg2rad(fb.ego_yaw_deg[1000:3000])
+    fb.ego_speed_mph[1000:3000] = 0.0  # standstill behind a stopped car (one NaN point)
+    fb.prev_n[1000:3000] = 0
+    fb.n_cars[1000:3000] = 1
+    with np.errstate(invalid="ignore"):  # a few of these yaws were poisoned above
+        fb.car_x[1000:3000, 0] = fb.ego_x[1000:3000] + 14.7 * np.cos(yaw)
+        fb.car_y[1000:3000, 0] = fb.ego_y[1000:3000] + 14.7 * np.sin(yaw)
+    fb.car_vx[1000:3000, 0] = 0.0
+    fb.car_vy[1000:3000, 0] = 0.0
+    df = pp.DeviceFrames(fb)
+    a = pp.DevicePlans(n, 6, diag=False, cars=False)
+    b = pp.DevicePlans(n, 6, diag=False, cars=False)
+    pp.plan_batch(gmap, df, a)
+    want = pp.stats_batch(a).cpu().numpy()
+    got = pp.plan_stats_batch(gmap, df, b).cpu().numpy()
+    assert np.array_equal(got, want), (got, want)
+    assert got[0] == n and got[1] < 50 * n  # some short paths are in there
