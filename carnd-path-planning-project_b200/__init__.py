@@ -30,7 +30,7 @@ MAP_CSV = os.path.join(ROOT, "data", "highway_map.csv")
 
 # every symbol include/pp.h declares (tests check the library exports them all)
 EXPORTS = [
-    "pp_version", "pp_strerror", "pp_last_cuda_error", "pp_device_count", "pp_config_default",
+    "pp_version", "pp_init", "pp_strerror", "pp_last_cuda_error", "pp_device_count", "pp_config_default",
     "pp_map_create", "pp_map_create_from_csv", "pp_map_destroy", "pp_map_num_waypoints",
     "pp_map_table", "pp_plan_batch", "pp_plan_batch_host", "pp_stats_batch",
     "pp_set_kernel_variant", "pp_launch_count", "pp_distancesq_pt_seg_batch",

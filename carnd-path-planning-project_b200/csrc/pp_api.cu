@@ -16,10 +16,12 @@
 // CUDA_DEVICE_MAX_CONNECTIONS hardware work queues, 8 by default: with more streams than queues
 // two independent streams share one and serialise, differently from run to run (the closed-loop
 // rollout job measured anywhere between 62 and 217 M ego-frames/s; with 32 queues 200-207 M,
-// profiles/probe_connections.sh).  The variable is read when the CUDA context is created, so it
-// is set when this library is loaded — unless the process already chose a value.
-__attribute__((constructor)) static void pp_more_work_queues() {
-  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+// profiles/probe_connections.sh).  The variable is read when the CUDA context is created, so a
+// process that wants the extra queues calls pp_init() before its first CUDA call (or exports the
+// variable itself).  The library never touches the environment on its own.
+extern "C" int pp_init(void) {
+  if (setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0) != 0) return PP_E_ARG;
+  return PP_OK;
 }
 
 namespace {
@@ -39,6 +41,29 @@ void set_cuda_error(const char *what, int cuda_err, const char *text) {
 }
 
 void count_launch(int n) { g_launches += n; }
+
+int check_map_device(const pp_map *map, const char *who) {
+  if (!map) return PP_E_ARG;
+  if (!map->dev_table) {
+    set_cuda_error(who, 0, "map has no device table (no usable CUDA device)");
+    return PP_E_CUDA;  // there is no CPU planning path
+  }
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_cuda_error("cudaGetDevice", (int)e, cudaGetErrorString(e));
+    cudaGetLastError();
+    return PP_E_CUDA;
+  }
+  if (dev != map->device) {
+    char msg[160];
+    std::snprintf(msg, sizeof msg, "map lives on device %d but device %d is current", map->device,
+                  dev);
+    set_cuda_error(who, 0, msg);
+    return PP_E_ARG;
+  }
+  return PP_OK;
+}
 
 int upload_map(pp_map *m) {
   int dev = 0;
@@ -318,6 +343,10 @@ extern "C" int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const
                         "");
     return PP_E_CUDA;
   }
+  {
+    const int rc = ppi::check_map_device(map, "pp_plan_batch_host");
+    if (rc != PP_OK) return rc;
+  }
   if (in->max_cars < 0 || in->max_cars > PP_MAX_CARS) return PP_E_RANGE;
   if (n_frames == 0) return PP_OK;
   const size_t mc = (size_t)in->max_cars;
@@ -369,6 +398,16 @@ extern "C" int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const
     sg.out_bytes = out_bpf;
   }
 
+  // Nothing may still be writing into the caller's buffers when this returns, whatever the
+  // outcome: a failure below joins the streams before it reports.
+  struct Join {
+    Staging &sg;
+    ~Join() {
+      for (int i = 0; i < kStreams; i++)
+        if (sg.streams[i]) cudaStreamSynchronize(sg.streams[i]);
+      cudaGetLastError();
+    }
+  } join_on_exit{sg};
   int slot = 0;
   int64_t lo = 0;
   for (size_t ci = 0; ci < sizes.size(); lo += sizes[ci], ci++, slot = (slot + 1) % kStreams) {

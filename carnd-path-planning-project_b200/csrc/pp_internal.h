@@ -27,6 +27,10 @@ int upload_map(pp_map *m);
 void free_map_device(pp_map *m);
 
 void set_cuda_error(const char *what, int cuda_err, const char *text);
+// PP_OK when the map's device table lives on the CURRENT device; PP_E_CUDA when the map has no
+// device table, PP_E_ARG when it was created on another device (using it would dereference a
+// foreign device pointer inside a kernel and poison the context).
+int check_map_device(const pp_map *map, const char *who);
 
 // pp_plan.cu: the pipeline with caller-owned scratch (see there)
 size_t plan_scratch_bytes(int64_t n_frames, int max_cars);

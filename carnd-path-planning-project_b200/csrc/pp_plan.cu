@@ -33,8 +33,10 @@
 // the pipeline (tests/test_gpu_parity.py).
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "pp_device.cuh"
@@ -99,9 +101,8 @@ struct SumOut {
 
 PPD_INLINE double ctx_dt0(const FrameCtx &c) { return c.nprev ? PP_PREV_KEEP / 50.0 : 0.0; }
 
-PPD_INLINE FrameCtx stage_prep(const MapView &m, const pp_config &cfg, const pp_frames &in,
-                               int64_t f) {
-  FrameCtx c;
+// Ego state from the previous path or the telemetry (:1254-1282); (svx, svy) = speed vector.
+PPD_INLINE void ego_state(const pp_frames &in, int64_t f, FrameCtx &c, double &svx, double &svy) {
   c.flags = 0;
   c.x = in.ego_x[f];
   c.y = in.ego_y[f];
@@ -109,7 +110,8 @@ PPD_INLINE FrameCtx stage_prep(const MapView &m, const pp_config &cfg, const pp_
   c.speed /= 2.237;  // :1239
   c.acc = 0;
   c.nprev = 0;
-  double svx = 0, svy = 0;
+  svx = 0;
+  svy = 0;
   if (in.prev_n[f] >= PP_PREV_KEEP) {  // :1261-1282
     const double *px = in.prev_x + f * PP_PREV_KEEP;
     const double *py = in.prev_y + f * PP_PREV_KEEP;
@@ -128,7 +130,11 @@ PPD_INLINE FrameCtx stage_prep(const MapView &m, const pp_config &cfg, const pp_
   } else {
     c.flags |= PP_F_COLD_START;
   }
-  init_reference(m, c.x, c.y, c.rs);  // :1299
+}
+
+// Ego lane matching + speed projection (:1302-1320), given c.rs.
+PPD_INLINE void ego_match(const MapView &m, const pp_config &cfg, FrameCtx &c, double svx,
+                          double svy) {
   Match em = lane_match(m, c.rs, c.x, c.y);  // :1302-1307
   if (!em.ok) {
     c.flags |= PP_F_EGO_MATCH_FAIL;
@@ -142,6 +148,15 @@ PPD_INLINE FrameCtx stage_prep(const MapView &m, const pp_config &cfg, const pp_
   project_speed(m, svx, svy, c.rs.wp, c.vs, c.vd);  // :1313
   if (c.acc > cfg.maximum_acc) c.acc = cfg.maximum_acc;  // :1319-1320
   if (c.acc < -cfg.maximum_acc) c.acc = -cfg.maximum_acc;
+}
+
+PPD_INLINE FrameCtx stage_prep(const MapView &m, const pp_config &cfg, const pp_frames &in,
+                               int64_t f) {
+  FrameCtx c;
+  double svx, svy;
+  ego_state(in, f, c, svx, svy);
+  init_reference(m, c.x, c.y, c.rs);  // :1299
+  ego_match(m, cfg, c, svx, svy);
   return c;
 }
 
@@ -201,22 +216,57 @@ PPD_INLINE void behav_init(Behav &b, const pp_config &cfg) {
   cand_init(b.tl1);
   cand_init(b.tl2);
 }
-PPD_INLINE void behav_add(Behav &b, const pp_config &cfg, const FrameCtx &c, int tl_in, int id,
-                          int j, const CarRes &car, uint32_t &flags) {
-  if (car.lane < 0) {  // :1336-1340 dropped from the map
+// One matched car, given its predicted position (s0, d0) = (s + vs dt0, d + vd dt0) (:67-70).
+PPD_INLINE void behav_add_pred(Behav &b, const pp_config &cfg, int ego_lane, double ego_s,
+                               double ego_vs, double ego_d, int tl_in, int id, int j, int car_lane,
+                               double s0, double car_vs, double d0, uint32_t &flags) {
+  if (car_lane < 0) {  // :1336-1340 dropped from the map
     flags |= PP_F_CAR_DROPPED;
     return;
   }
-  const double dt0 = ctx_dt0(c);
-  lane_stats_add(b.ls, cfg, id, car.lane, car.s, car.vs, c.lane, tl_in, c.s, c.vs, dt0, flags);
-  const double s0 = car.s + car.vs * dt0;
-  const double d0 = car.d + car.vd * dt0;
-  if (s0 > c.s && fabs(d0 - c.d) < 3) cand_offer(b.own, s0, id, j);
-  if (s0 >= c.s - cfg.car_length - cfg.safety_distance) {  // :1402
+  lane_stats_add_pred(b.ls, cfg, id, car_lane, s0, car_vs, ego_lane, tl_in, ego_s, ego_vs, flags);
+  if (s0 > ego_s && fabs(d0 - ego_d) < 3) cand_offer(b.own, s0, id, j);
+  if (s0 >= ego_s - cfg.car_length - cfg.safety_distance) {  // :1402
     if (fabs(d0 - lane_center_offset(0)) < 3) cand_offer(b.tl0, s0, id, j);
     if (fabs(d0 - lane_center_offset(1)) < 3) cand_offer(b.tl1, s0, id, j);
     if (fabs(d0 - lane_center_offset(2)) < 3) cand_offer(b.tl2, s0, id, j);
   }
+}
+PPD_INLINE void behav_add(Behav &b, const pp_config &cfg, const FrameCtx &c, int tl_in, int id,
+                          int j, const CarRes &car, uint32_t &flags) {
+  const double dt0 = ctx_dt0(c);
+  behav_add_pred(b, cfg, c.lane, c.s, c.vs, c.d, tl_in, id, j, car.lane, car.s + car.vs * dt0,
+                 car.vs, car.d + car.vd * dt0, flags);
+}
+
+// Every reduction of Behav is a lexicographic minimum, an AND or an OR, so partial results
+// over disjoint sets of cars combine in any order: `b` += the partial result held by lane
+// (own ^ mask); applied for every bit of a lane group this is a butterfly that leaves the
+// group's total in each of its lanes (several lanes reduce one frame's cars, k_front).
+PPD_INLINE void cand_merge_xor(Cand &c, int mask) {
+  const double s0 = __shfl_xor_sync(0xffffffffu, c.s0, mask);
+  const int id = __shfl_xor_sync(0xffffffffu, c.id, mask);
+  const int j = __shfl_xor_sync(0xffffffffu, c.j, mask);
+  if (id != -1) cand_offer(c, s0, id, j);
+}
+PPD_INLINE void behav_merge_xor(Behav &b, uint32_t &flags, int mask) {
+#pragma unroll
+  for (int l = 0; l < 3; l++) {
+    const double os = __shfl_xor_sync(0xffffffffu, b.ls.next_s[l], mask);
+    const int oid = __shfl_xor_sync(0xffffffffu, b.ls.next_id[l], mask);
+    const double osp = __shfl_xor_sync(0xffffffffu, b.ls.speed[l], mask);
+    // (a real entry always has s < 1000 = the default, so the default never wins a tie)
+    const bool take = os < b.ls.next_s[l] || (os == b.ls.next_s[l] && oid < b.ls.next_id[l]);
+    b.ls.next_s[l] = take ? os : b.ls.next_s[l];
+    b.ls.next_id[l] = take ? oid : b.ls.next_id[l];
+    b.ls.speed[l] = take ? osp : b.ls.speed[l];
+  }
+  b.ls.open &= __shfl_xor_sync(0xffffffffu, b.ls.open, mask);
+  flags |= __shfl_xor_sync(0xffffffffu, flags, mask);
+  cand_merge_xor(b.own, mask);
+  cand_merge_xor(b.tl0, mask);
+  cand_merge_xor(b.tl1, mask);
+  cand_merge_xor(b.tl2, mask);
 }
 
 // ---------------------------------------------------------------------------
@@ -357,6 +407,8 @@ plan_fused(const double *__restrict__ map_table, int n_wp, const __grid_constant
 // Per-chunk scratch in HBM (SoA, one entry per frame / per car slot).
 struct Scratch {
   double *x, *y, *speed, *acc, *s, *d, *vs, *vd, *ratio;  // ratio: [3][n]
+  double *bh_d;   // tiled pipeline: the reduced Behav of every frame, [kBehavD][n]
+  int32_t *bh_i;  // [kBehavI][n]
   int32_t *wp, *lane, *nprev;
   uint32_t *flags;
   double *car_s, *car_d, *car_vs, *car_vd;  // [n][max_cars]
@@ -420,7 +472,51 @@ Scratch carve_scratch(char *base, int64_t n, int mc) {
   s.e_flags = (uint32_t *)take(N * 4);
   s.slow_qa = s.slow_qb = s.slow_na = s.slow_nb = s.dbg = nullptr;  // set per chunk by the caller
   s.xsum = nullptr;
+  s.bh_d = nullptr;
+  s.bh_i = nullptr;
   s.n = n;
+  return s;
+}
+
+// Scratch of the tiled pipeline (variant 3): the ego context from k_prep (104 B per frame), the
+// reduced Behav from k_cars_t (120 B), the emission state from k_decide_t.  The row stride is a
+// multiple of 32 frames.
+constexpr int kBehavDoubles = 10, kBehavInts = 10;
+int64_t scratch3_stride(int64_t n) { return (n + 31) / 32 * 32; }
+size_t scratch3_bytes(int64_t n) {
+  const size_t N = (size_t)scratch3_stride(n);
+  return N * (11 * 8 + 4 * 4 + kBehavDoubles * 8 + kBehavInts * 4 + (size_t)kEstRows * 8 + 3 * 4) +
+         40 * 256;
+}
+Scratch carve_scratch3(char *base, int64_t n) {
+  Scratch s = {};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char *p = base + off;
+    off += (bytes + 255) & ~(size_t)255;
+    return p;
+  };
+  const size_t N = (size_t)scratch3_stride(n);
+  s.x = (double *)take(N * 8);
+  s.y = (double *)take(N * 8);
+  s.speed = (double *)take(N * 8);
+  s.acc = (double *)take(N * 8);
+  s.s = (double *)take(N * 8);
+  s.d = (double *)take(N * 8);
+  s.vs = (double *)take(N * 8);
+  s.vd = (double *)take(N * 8);
+  s.ratio = (double *)take(3 * N * 8);
+  s.wp = (int32_t *)take(N * 4);
+  s.lane = (int32_t *)take(N * 4);
+  s.nprev = (int32_t *)take(N * 4);
+  s.flags = (uint32_t *)take(N * 4);
+  s.bh_d = (double *)take((size_t)kBehavDoubles * N * 8);
+  s.bh_i = (int32_t *)take((size_t)kBehavInts * N * 4);
+  s.est = (double *)take((size_t)kEstRows * N * 8);
+  s.e_np = (int32_t *)take(N * 4);
+  s.e_nk = (int32_t *)take(N * 4);
+  s.e_flags = (uint32_t *)take(N * 4);
+  s.n = (int64_t)N;
   return s;
 }
 
@@ -501,7 +597,7 @@ k_cars(const double *__restrict__ map_table, int n_wp, const __grid_constant__ p
       const bool in_range = t < total;
       const int64_t tc = in_range ? t : total - 1;
       const unsigned xi = r0 + (unsigned)(tc - base);
-      const unsigned qi = __umulhi(xi, mc_magic);
+      const unsigned qi = mc == 1 ? xi : __umulhi(xi, mc_magic);  // (the magic wraps to 0 for 1)
       const int64_t f = f0 + qi;
       const int j = (int)(xi - qi * (unsigned)mc);
       const int nc = in.n_cars[f];
@@ -536,7 +632,7 @@ k_cars(const double *__restrict__ map_table, int n_wp, const __grid_constant__ p
     for (int g = lane; g < n_valid; g += 32) {
       const unsigned oi = order[g];
       const int64_t t = base + oi;
-      const unsigned qi = __umulhi(r0 + oi, mc_magic);
+      const unsigned qi = mc == 1 ? r0 + oi : __umulhi(r0 + oi, mc_magic);
       const int64_t f = f0 + qi;
       const int j = (int)(r0 + oi - qi * (unsigned)mc);
       RefState rs;
@@ -603,69 +699,6 @@ PPD_INLINE void reduce_cars(const pp_config &cfg, const pp_frames &in, const Scr
     if (j + 1 < nc) fetch(j + 1);
     behav_add(b, cfg, c, tl_in, id, j, r, flags);
   }
-}
-
-// Decision + trajectory set-up + spline fit (one thread per frame).  Frames whose
-// trajectory is the ordinary spline emission hand their state to k_emit; the
-// rest (angle-based generator, :848) go to the queue of k_slow.
-__global__ void __launch_bounds__(kBlock, PP_DECIDE_MINB)
-k_decide(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
-         const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
-         const __grid_constant__ Scratch sc, int64_t n) {
-  // shared memory holds the spline sweep's rows (one column per thread); the map is only
-  // touched by the handful of get_lane_pos steps per frame and is read through L1 instead
-  extern __shared__ __align__(16) double s_rows[];  // [PPD_SWEEP_ROWS * PPD_TAILK][blockDim.x]
-  MapView m;
-  m.t = map_table + PPD_PAD * PP_MAP_STRIDE;
-  m.n = n_wp;
-  m.pad_lo = n_wp < PPD_PAD ? n_wp : PPD_PAD;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  long long xacc = 0;  // checksum of the kept points (= the stored previous points, :578)
-  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += stride) {
-    FrameCtx c;
-    load_ctx(sc, f, c);
-    uint32_t flags = c.flags;
-    const int tl_in = in.target_lane_in[f];
-    Behav b;
-    reduce_cars(cfg, in, sc, f, c, tl_in, b, flags);
-    const Decision d = stage_decide(cfg, in, out, f, c, b, tl_in, flags);
-    flags = d.flags;
-    if (sc.xsum) {
-      for (int i = 0; i < c.nprev; i++)
-        xacc += fx_point(in.prev_x[f * PP_PREV_KEEP + i], in.prev_y[f * PP_PREV_KEEP + i]);
-    }
-    double *e = sc.est + f;
-    KnotSweep sw;
-    sw.init(s_rows + threadIdx.x, blockDim.x, e, sc.n, kEstHead);
-    TrajFrame tf;
-    traj_setup(m, cfg, c.rs, in.prev_x + f * PP_PREV_KEEP, in.prev_y + f * PP_PREV_KEEP, c.nprev,
-               c.x, c.y, in.ego_yaw_deg[f], d.target_lane, c.d, c.vd, d.sc,
-               out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN, flags, sw, tf);
-    e[0 * sc.n] = d.sc.start;
-    e[1 * sc.n] = d.sc.target;
-    e[2 * sc.n] = d.sc.time;
-    e[3 * sc.n] = tf.cx;
-    e[4 * sc.n] = tf.cy;
-    e[5 * sc.n] = tf.ca;
-    e[6 * sc.n] = tf.sa;
-    sc.e_np[f] = tf.np;
-    if (tf.fallback) {  // :848 the angle-based generator: its own (converged) kernel
-#pragma unroll
-      for (int k = 0; k < 6; k++) {
-        e[(kEstHead + k) * sc.n] = tf.cpx[k];
-        e[(kEstHead + 6 + k) * sc.n] = tf.cpy[k];
-      }
-      sc.e_nk[f] = kEstFallback | tf.ncp;
-      sc.e_flags[f] = flags | PP_F_FALLBACK;
-      sc.slow_qa[atomicAdd(sc.slow_na, 1)] = (int32_t)f;
-      continue;
-    }
-    const int r0 = sw.r0;
-    const int cnt = sw.solve(tf.nk);  // a, b, c of the reachable rows -> emission state
-    sc.e_nk[f] = cnt | (r0 > 0 ? kEstPartial : 0);
-    sc.e_flags[f] = flags;
-  }
-  if (sc.xsum) xsum_commit(sc.xsum, xacc);
 }
 
 template <class S>
@@ -819,6 +852,463 @@ k_slow(const double *__restrict__ map_table, int n_wp, const __grid_constant__ p
   }
 }
 
+// ===========================================================================
+// Variant 3: the tiled pipeline.  Same phases as variant 2, but a frame TILE is the unit of
+// memory traffic where that pays: the cars of a warp's frames arrive in shared memory by TMA
+// bulk copies and their results never leave the SM (the reductions of LaneChangePlanner and
+// the followed-car selection run in the kernel that matched the cars: 120 B per frame go on
+// instead of 36 B per car written and read back), and the decision kernel gets the previous
+// points of its 128 frames by one bulk copy per coordinate and copies the kept points out of
+// the same tile.
+//
+//   k_prep     (as variant 2) one thread per frame
+//   k_cars_t   one WARP per tile of F = min(32, 256 / max_cars) consecutive frames: the
+//              tile's cars bulk-copied into shared memory, counting-sorted by expected walk
+//              length and matched (lane = car), results written over the inputs in place;
+//              then the per-frame reductions (:377-445, :1388-1410; G lanes per frame,
+//              merged with a shuffle butterfly when traffic is dense)
+//   k_decide_t one thread per frame, tiles of 128: lane decision, veto, followed cars,
+//              LimitSpeed, SpeedController (:1355-1438), TrajectoryBuilder set-up and the
+//              tk::spline fit (:565-904)
+//   k_emit     (as variant 2)
+//
+// Measured and dropped (profiles/r2_probe_*.log): one fused front kernel (ego state + cars +
+// reductions + decision; the state it carries across the car phase spills, 1.82 ms against
+// 1.49 ms for the separate kernels), knot rows by TMA into the emission kernel (0.92 against
+// 0.87 ms: a block-synchronous tile loop exposes the slowest lane and the load latency once
+// per tile) and per-lane 80-byte bulk stores of the emitted points (1.01 ms: a bulk copy is
+// issued lane by lane, 64 of them replace 10 vector stores).
+// ===========================================================================
+struct CarsGeom {
+  int F;        // frames per warp tile
+  int G;        // lanes per frame in the reduction (power of two, F * G <= 32)
+  int T;        // car slots per tile (F * max_cars rounded up to even)
+  int Cg;       // max_cars rounded up to a multiple of G
+  int warp_bytes;  // shared memory per warp
+  unsigned magic;  // ceil(2^16 / max_cars): i / max_cars for i < 256
+  int bulk;     // car arrays are 16-byte aligned: tiles come by TMA
+};
+
+// per-warp shared memory: car[4][T] doubles | 8 per-frame double arrays [Fc] | 5 per-frame int
+// arrays [Fc] | hist[32] ints | order[256] bytes | mbarrier     (Fc = F rounded up to even)
+__host__ __device__ inline int cars_warp_bytes(int T, int F) {
+  const int Fc = (F + 1) & ~1;
+  const int b = 4 * T * 8 + 8 * Fc * 8 + 5 * Fc * 4 + 32 * 4 + 256 + 16;
+  return (b + 15) & ~15;
+}
+// what a matched car contributes to its frame's reductions, packed next to its lane
+constexpr unsigned kFactCloses = 1u << 31;  // closes its lane (:405-444)
+constexpr unsigned kFactOwn = 1u << 27;     // ahead in the ego's corridor (:1388-1398)
+constexpr unsigned kFactTl0 = 1u << 28;     // candidate for target lane 0 / 1 / 2 (:1402-1410)
+constexpr unsigned kFactFlags = PP_F_CLOSED_RANGE | PP_F_CLOSED_AHEAD | PP_F_CLOSED_BEHIND;
+static_assert((kFactFlags & (kFactCloses | (15u << 27))) == 0, "fact bits overlap the flags");
+
+constexpr int kCarRounds = 8;  // 32-item rounds per tile (<= 256 car slots)
+static_assert(kBehavDoubles == 10 && kBehavInts == 10, "behav_store / behav_load layout");
+
+PPD_INLINE void behav_store(const Scratch &sc, int64_t f, const Behav &b, uint32_t flags) {
+  double *d = sc.bh_d + f;
+  int32_t *i = sc.bh_i + f;
+  const int64_t n = sc.n;
+#pragma unroll
+  for (int l = 0; l < 3; l++) {
+    d[l * n] = b.ls.next_s[l];
+    d[(3 + l) * n] = b.ls.speed[l];
+  }
+  d[6 * n] = b.own.s0;
+  d[7 * n] = b.tl0.s0;
+  d[8 * n] = b.tl1.s0;
+  d[9 * n] = b.tl2.s0;
+  i[0 * n] = (int32_t)b.ls.open;
+  i[1 * n] = (int32_t)flags;
+  i[2 * n] = b.own.id;
+  i[3 * n] = b.own.j;
+  i[4 * n] = b.tl0.id;
+  i[5 * n] = b.tl0.j;
+  i[6 * n] = b.tl1.id;
+  i[7 * n] = b.tl1.j;
+  i[8 * n] = b.tl2.id;
+  i[9 * n] = b.tl2.j;
+}
+PPD_INLINE void behav_load(const Scratch &sc, const pp_config &cfg, int64_t f, Behav &b,
+                           uint32_t &flags) {
+  const double *d = sc.bh_d + f;
+  const int32_t *i = sc.bh_i + f;
+  const int64_t n = sc.n;
+  behav_init(b, cfg);
+#pragma unroll
+  for (int l = 0; l < 3; l++) {
+    b.ls.next_s[l] = d[l * n];
+    b.ls.speed[l] = d[(3 + l) * n];
+  }
+  b.own.s0 = d[6 * n];
+  b.tl0.s0 = d[7 * n];
+  b.tl1.s0 = d[8 * n];
+  b.tl2.s0 = d[9 * n];
+  b.ls.open = (unsigned)i[0 * n];
+  flags |= (uint32_t)i[1 * n];
+  b.own.id = i[2 * n];
+  b.own.j = i[3 * n];
+  b.tl0.id = i[4 * n];
+  b.tl0.j = i[5 * n];
+  b.tl1.id = i[6 * n];
+  b.tl1.j = i[7 * n];
+  b.tl2.id = i[8 * n];
+  b.tl2.j = i[9 * n];
+}
+
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads, 1)
+k_cars_t(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
+         const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
+         const __grid_constant__ Scratch sc, int64_t n, const __grid_constant__ CarsGeom g) {
+  extern __shared__ __align__(16) double s_dyn[];
+  const MapView m = stage_map(s_dyn, map_table, n_wp);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  char *wbase = reinterpret_cast<char *>(s_dyn) + map_stage_bytes(n_wp) + (size_t)wib * g.warp_bytes;
+  double *car0 = reinterpret_cast<double *>(wbase);  // x -> predicted s
+  double *car1 = car0 + g.T;                          // y -> predicted d
+  double *car2 = car1 + g.T;                          // vx -> vs
+  double *car3 = car2 + g.T;                          // vy -> lane (int)
+  const int Fc = (g.F + 1) & ~1;
+  double *fx = car3 + g.T, *fy = fx + Fc, *fr0 = fy + Fc, *fr1 = fr0 + Fc, *fr2 = fr1 + Fc;
+  double *fes = fr2 + Fc, *fevs = fes + Fc, *fed = fevs + Fc;  // ego s, vs, d
+  int *fwp = reinterpret_cast<int *>(fed + Fc), *fnc = fwp + Fc, *fnp = fnc + Fc;
+  int *fel = fnp + Fc, *ftl = fel + Fc;  // ego lane, incoming target lane
+  int *hist = ftl + Fc;
+  unsigned char *order = reinterpret_cast<unsigned char *>(hist + 32);
+  unsigned long long *bar_p = reinterpret_cast<unsigned long long *>(
+      (reinterpret_cast<uintptr_t>(order + 256) + 7) & ~(uintptr_t)7);
+  const unsigned bar = smem_addr(bar_p);
+  if (lane == 0) mbar_init(bar, 1);
+  __syncwarp();
+  const int mc = in.max_cars, F = g.F, G = g.G;
+  const Rcp racc = rcp_make(cfg.relaxed_acc);
+  const int64_t n_tiles = (n + F - 1) / F;
+  const int64_t warps = (int64_t)gridDim.x * (kThreads / 32);
+  unsigned phase = 0;
+  for (int64_t tile = (int64_t)blockIdx.x * (kThreads / 32) + wib; tile < n_tiles; tile += warps) {
+    const int64_t f0 = tile * F;
+    const int nf = (int)((n - f0) < F ? (n - f0) : F);
+    const int items = nf * mc;
+    const int64_t cb0 = f0 * mc;
+    // ---- the tile's cars: one bulk copy per array (ordinary loads when unaligned)
+    const bool bulk = g.bulk && !(items & 1);
+    if (bulk) {
+      if (lane == 0) {
+        const unsigned bytes = (unsigned)items * 8u;
+        mbar_expect_tx(bar, 4u * bytes);
+        bulk_g2s(smem_addr(car0), in.car_x + cb0, bytes, bar);
+        bulk_g2s(smem_addr(car1), in.car_y + cb0, bytes, bar);
+        bulk_g2s(smem_addr(car2), in.car_vx + cb0, bytes, bar);
+        bulk_g2s(smem_addr(car3), in.car_vy + cb0, bytes, bar);
+      }
+    } else {
+      for (int i = lane; i < items; i += 32) {
+        car0[i] = in.car_x[cb0 + i];
+        car1[i] = in.car_y[cb0 + i];
+        car2[i] = in.car_vx[cb0 + i];
+        car3[i] = in.car_vy[cb0 + i];
+      }
+    }
+    // ---- what the car lanes need of their frames (lane = frame here)
+    if (lane < nf) {
+      const int64_t f = f0 + lane;
+      fx[lane] = sc.x[f];
+      fy[lane] = sc.y[f];
+      fr0[lane] = sc.ratio[f];
+      fr1[lane] = sc.ratio[sc.n + f];
+      fr2[lane] = sc.ratio[2 * sc.n + f];
+      fwp[lane] = sc.wp[f];
+      const int nc = in.n_cars[f];
+      fnc[lane] = nc > mc ? mc : nc;
+      fnp[lane] = sc.nprev[f];
+      fes[lane] = sc.s[f];
+      fevs[lane] = sc.vs[f];
+      fed[lane] = sc.d[f];
+      fel[lane] = sc.lane[f];
+      ftl[lane] = in.target_lane_in[f];
+    }
+    hist[lane] = 0;
+    __syncwarp();
+    if (bulk) {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+    }
+    // ---- bin the cars by expected walk length (distance to the ego in units of the local
+    // segment length); the proxy only orders the work
+    int key[kCarRounds];
+#pragma unroll
+    for (int k = 0; k < kCarRounds; k++) {
+      key[k] = kBins;
+      if (k * 32 < items) {
+        const int i = k * 32 + lane;
+        const int ic = i < items ? i : items - 1;
+        const int fl = (int)(((unsigned)ic * g.magic) >> 16);
+        const int j = ic - fl * mc;
+        const float dx = (float)(car0[ic] - fx[fl]), dy = (float)(car1[ic] - fy[fl]);
+        const float len = (float)row(m, fwp[fl])[11];  // centre lane's segment length
+        const float q = sqrtf(dx * dx + dy * dy) / len;
+        const int bin = q < (float)(kBins - 1) ? (int)q : kBins - 1;  // NaN -> last bin
+        key[k] = ((i < items) & (j < fnc[fl])) ? bin : kBins;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kCarRounds; k++)
+      if (k * 32 < items) key[k] |= atomicAdd(&hist[key[k]], 1) << 8;
+    __syncwarp();
+    const int cnt = hist[lane];
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    __syncwarp();
+    hist[lane] = incl - cnt;
+    __syncwarp();
+    const int n_valid = hist[kBins];
+#pragma unroll
+    for (int k = 0; k < kCarRounds; k++)
+      if (k * 32 < items) {
+        const int pos = hist[key[k] & 0xff] + (key[k] >> 8);
+        if (pos < 256) order[pos] = (unsigned char)(k * 32 + lane);
+      }
+    __syncwarp();
+    // ---- match them, 32 of similar walk length at a time; results replace the inputs
+    for (int gi = lane; gi < n_valid; gi += 32) {
+      const int i = order[gi];
+      const int fl = (int)(((unsigned)i * g.magic) >> 16);
+      RefState rs;
+      rs.wp = fwp[fl];
+      rs.ratio[0] = fr0[fl];
+      rs.ratio[1] = fr1[fl];
+      rs.ratio[2] = fr2[fl];
+      const CarRes r = stage_car(m, rs, car0[i], car1[i], car2[i], car3[i]);
+      store_car(out, cb0 + i, r);
+      // its share of the frame's reductions, evaluated here where every lane has a car
+      const double dt0 = fnp[fl] ? PP_PREV_KEEP / 50.0 : 0.0;
+      const double s0 = r.s + r.vs * dt0;  // Car::predicted_s (:67)
+      const double d0 = r.d + r.vd * dt0;  // Car::predicted_d (:70)
+      double lane_speed = 0;
+      unsigned fw = 0;
+      if (r.lane >= 0) {
+        const double es = fes[fl];
+        const CarFacts cf = lane_car_facts(cfg, racc, r.lane, s0, r.vs, fel[fl], ftl[fl], es, fevs[fl]);
+        lane_speed = cf.lane_speed;
+        fw = cf.flags | (cf.closes ? kFactCloses : 0u);
+        if (s0 > es && fabs(d0 - fed[fl]) < 3) fw |= kFactOwn;             // :1392
+        if (s0 >= es - cfg.car_length - cfg.safety_distance) {             // :1402
+#pragma unroll
+          for (int l = 0; l < 3; l++)
+            if (fabs(d0 - lane_center_offset(l)) < 3) fw |= kFactTl0 << l;
+        }
+      }
+      car0[i] = s0;
+      car2[i] = lane_speed;
+      *reinterpret_cast<int2 *>(car3 + i) = make_int2(r.lane, (int)fw);
+    }
+    __syncwarp();
+    // ---- per-frame reductions (:377-445, :1388-1410).  Lanes fl G .. fl G + G - 1 share the
+    // cars of frame fl (lane k takes j = k mod G), visiting them from a lane-dependent start
+    // (spreads the banks); every reduction is order-free, so the partial results merge with a
+    // butterfly and lane k = 0 stores the frame's outcome.
+    {
+      const int Cg = g.Cg;
+      const int fl = lane / G, k = lane - fl * G;
+      const bool act = fl < nf;
+      const int64_t f = f0 + (act ? fl : 0);
+      uint32_t pflags = 0;
+      Behav bp;
+      behav_init(bp, cfg);
+      if (act) {
+        const double e_s = fes[fl];
+        const int e_nc = fnc[fl];
+        int j = (fl * G) % Cg + k;
+        if (j >= Cg) j -= Cg;
+        const int base = fl * mc;
+        const int32_t *ids = in.car_id + cb0 + base;
+        for (int q = 0; q < Cg; q += G) {
+          if (j < e_nc) {
+            const int2 w = *reinterpret_cast<const int2 *>(car3 + base + j);
+            const unsigned fw = (unsigned)w.y;
+            if (w.x < 0) {  // :1336-1340 dropped from the map
+              pflags |= PP_F_CAR_DROPPED;
+            } else {
+              const double s0 = car0[base + j];
+              const int id = ids[j];
+              pflags |= fw & kFactFlags;
+              lane_stats_take(bp.ls, id, w.x, s0, s0 > e_s, car2[base + j], (fw & kFactCloses) != 0);
+              if (fw & kFactOwn) cand_offer(bp.own, s0, id, j);
+              if (fw & kFactTl0) cand_offer(bp.tl0, s0, id, j);
+              if (fw & (kFactTl0 << 1)) cand_offer(bp.tl1, s0, id, j);
+              if (fw & (kFactTl0 << 2)) cand_offer(bp.tl2, s0, id, j);
+            }
+          }
+          j += G;
+          if (j >= Cg) j -= Cg;
+        }
+      }
+      for (int o = 1; o < G; o <<= 1) behav_merge_xor(bp, pflags, o);
+      if (act && k == 0) behav_store(sc, f, bp, pflags);
+    }
+    fence_async_smem();  // results were written where the next tile's bulk copies land
+    __syncwarp();
+  }
+}
+
+// Decision, trajectory set-up and spline fit, one thread per frame, tiles of kBlock frames:
+// the tile's previous points arrive by one bulk copy per coordinate while the threads reduce
+// their cars and decide, and the kept points of the result (= those previous points, :578)
+// leave from the same tile by bulk copies — as strided loads and stores of every lane's own
+// 80-byte rows these were 10 % of this kernel's stall samples and 0.1 ms per 1M frames.
+// kBehav: the reductions were done by k_cars_t (variant 3), else they run here over the
+// car-major scratch of k_cars.  Frames whose trajectory is the ordinary spline emission hand
+// their state to k_emit; the rest (angle-based generator, :848) are queued for k_fallback.
+template <bool kBehav>
+__global__ void __launch_bounds__(kBlock, PP_DECIDE_MINB)
+k_decide_t(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
+           const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
+           const __grid_constant__ Scratch sc, int64_t n, int bulk_in, int bulk_out) {
+  extern __shared__ __align__(16) double s_dyn[];
+  double *s_rows = s_dyn;                                      // [PPD_SWEEP_ROWS * PPD_TAILK][kBlock]
+  double *s_px = s_dyn + PPD_SWEEP_ROWS * PPD_TAILK * kBlock;  // [kBlock][10]
+  double *s_py = s_px + kBlock * PP_PREV_KEEP;
+  __shared__ __align__(8) unsigned long long s_bar;
+  const unsigned bar = smem_addr(&s_bar);
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  MapView m;
+  m.t = map_table + PPD_PAD * PP_MAP_STRIDE;
+  m.n = n_wp;
+  m.pad_lo = n_wp < PPD_PAD ? n_wp : PPD_PAD;
+  const int64_t n_tiles = (n + kBlock - 1) / kBlock;
+  long long xacc = 0;  // checksum of the kept points (= the stored previous points, :578)
+  unsigned phase = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t f0 = tile * kBlock;
+    const int nf = (int)((n - f0) < kBlock ? (n - f0) : kBlock);
+    const unsigned bytes = (unsigned)nf * PP_PREV_KEEP * 8u;  // a multiple of 16
+    if (bulk_in && threadIdx.x == 0) {
+      mbar_expect_tx(bar, 2u * bytes);
+      bulk_g2s(smem_addr(s_px), in.prev_x + f0 * PP_PREV_KEEP, bytes, bar);
+      bulk_g2s(smem_addr(s_py), in.prev_y + f0 * PP_PREV_KEEP, bytes, bar);
+    }
+    // (the decision needs nothing of the tile: it runs while the copy is in flight)
+    const int64_t f = f0 + threadIdx.x;
+    const bool own = threadIdx.x < nf;
+    FrameCtx c;
+    Decision d;
+    if (own) {
+      load_ctx(sc, f, c);
+      uint32_t flags = c.flags;
+      const int tl_in = in.target_lane_in[f];
+      Behav b;
+      if (kBehav)
+        behav_load(sc, cfg, f, b, flags);
+      else
+        reduce_cars(cfg, in, sc, f, c, tl_in, b, flags);
+      d = stage_decide(cfg, in, out, f, c, b, tl_in, flags);
+    }
+    if (bulk_in) {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+    } else {
+      for (int i = threadIdx.x; i < nf * PP_PREV_KEEP; i += kBlock) {
+        s_px[i] = in.prev_x[f0 * PP_PREV_KEEP + i];
+        s_py[i] = in.prev_y[f0 * PP_PREV_KEEP + i];
+      }
+      __syncthreads();
+    }
+    if (own) {
+      const double *px = s_px + threadIdx.x * PP_PREV_KEEP;
+      const double *py = s_py + threadIdx.x * PP_PREV_KEEP;
+      uint32_t flags = d.flags;
+      double *gx = out.next_x + f * PP_PATH_LEN, *gy = out.next_y + f * PP_PATH_LEN;
+      if (c.nprev) {  // result_points = prev_trajectory (:578): straight from the staged tile
+        if (bulk_out) {
+          bulk_s2g(gx, smem_addr(px), PP_PREV_KEEP * 8);
+          bulk_s2g(gy, smem_addr(py), PP_PREV_KEEP * 8);
+          bulk_commit();
+        }
+        if (sc.xsum) {
+#pragma unroll
+          for (int h = 0; h < PP_PREV_KEEP / 2; h++) {
+            const double2 qx = reinterpret_cast<const double2 *>(px)[h];
+            const double2 qy = reinterpret_cast<const double2 *>(py)[h];
+            xacc += fx_point(qx.x, qy.x) + fx_point(qx.y, qy.y);
+          }
+        }
+      }
+      double *e = sc.est + f;
+      KnotSweep sw;
+      sw.init(s_rows + threadIdx.x, kBlock, e, sc.n, kEstHead);
+      TrajFrame tf;
+      traj_setup<true>(m, cfg, c.rs, px, py, c.nprev, c.x, c.y, in.ego_yaw_deg[f], d.target_lane,
+                       c.d, c.vd, d.sc, bulk_out ? nullptr : gx, bulk_out ? nullptr : gy, flags, sw,
+                       tf);
+      e[0 * sc.n] = d.sc.start;
+      e[1 * sc.n] = d.sc.target;
+      e[2 * sc.n] = d.sc.time;
+      e[3 * sc.n] = tf.cx;
+      e[4 * sc.n] = tf.cy;
+      e[5 * sc.n] = tf.ca;
+      e[6 * sc.n] = tf.sa;
+      sc.e_np[f] = tf.np;
+      if (tf.fallback) {  // :848 the angle-based generator: its own (converged) kernel
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          e[(kEstHead + k) * sc.n] = tf.cpx[k];
+          e[(kEstHead + 6 + k) * sc.n] = tf.cpy[k];
+        }
+        sc.e_nk[f] = kEstFallback | tf.ncp;
+        sc.e_flags[f] = flags | PP_F_FALLBACK;
+        sc.slow_qa[atomicAdd(sc.slow_na, 1)] = (int32_t)f;
+      } else {
+        const int r0 = sw.r0;
+        const int cnt = sw.solve(tf.nk);  // a, b, c of the reachable rows -> emission state
+        sc.e_nk[f] = cnt | (r0 > 0 ? kEstPartial : 0);
+        sc.e_flags[f] = flags;
+      }
+      if (bulk_out) bulk_wait_read();  // the tile is overwritten by the next load
+    }
+    fence_async_smem();
+    __syncthreads();
+  }
+  if (bulk_out) bulk_wait_all();
+  if (sc.xsum) xsum_commit(sc.xsum, xacc);
+}
+
+// The complete path for the frames k_emit gave up on (tiled pipeline): re-planned from their inputs alone
+// (a few hundred per million; every output is rewritten with the same values, the trajectory
+// by the complete emission loop), one frame per warp.
+__global__ void __launch_bounds__(kBlock)
+k_slow_t(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
+         const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
+         unsigned long long *xsum, const int32_t *__restrict__ queue,
+         const int32_t *__restrict__ queue_n) {
+  const int count = *queue_n;
+  const int per_block = kBlock / kSlowSpread;
+  if ((int64_t)blockIdx.x * per_block >= count) return;
+  extern __shared__ __align__(16) double s_map[];
+  const MapView m = stage_map(s_map, map_table, n_wp);
+  if (threadIdx.x % kSlowSpread) return;
+  const int64_t stride = (int64_t)gridDim.x * per_block;
+  for (int64_t q = (int64_t)blockIdx.x * per_block + threadIdx.x / kSlowSpread; q < count;
+       q += stride) {
+    const int64_t f = queue[q];
+    plan_one_frame(m, cfg, in, out, f);
+    if (xsum) {  // the new points (the kept ones were counted by k_decide_t)
+      long long xacc = 0;
+      const int np = out.n_points[f];
+      const int nprev = in.prev_n[f] >= PP_PREV_KEEP ? PP_PREV_KEEP : 0;
+      for (int i = nprev; i < np; i++)
+        xacc += fx_point(out.next_x[f * PP_PATH_LEN + i], out.next_y[f * PP_PATH_LEN + i]);
+      if (xacc) atomicAdd(xsum, (unsigned long long)xacc);
+    }
+  }
+}
+
 // ---- aggregate statistics: exact int64 sums -----------------
 // HBM bound (re-reads the plans: 828 B/frame).  The trajectories are read as one
 // flat array (coalesced; the owning frame's n_points masks the padding), the
@@ -936,8 +1426,9 @@ stats_kernel(const __grid_constant__ pp_plans p, int64_t n, unsigned long long *
     if (s_acc[i]) atomicAdd(&stats[i], s_acc[i]);
 }
 
-int g_variant = 0;
-int g_sm_count = 0;
+// process-wide knobs (tests, bench.py, profiles/): plain loads and stores of an atomic
+std::atomic<int> g_variant{0};
+std::atomic<int> g_sm_count{0};
 
 // ---- side stream for the rare-frame kernel (one per host thread and device)
 struct Side {
@@ -1001,8 +1492,9 @@ Side &side_for(cudaStream_t st) {
 // ---- pipes: a batch of several chunks is planned on kMaxPipes internal streams at once
 // (chunk i on pipe i % pipes).  Each kernel of the pipeline is sized for the whole GPU, but its
 // last wave and its divergent tails leave SMs idle; with a second chunk in flight those slots
-// run the other chunks' kernels (measured per 1M frames: 3.53 ms with one pipe, 3.02 with two,
-// 2.85 with four chunks of 262,144 frames in flight; more or smaller chunks do not help).
+// run the other chunks' kernels (measured per 1M frames, DESIGN.md §3: 3.13 ms with one pipe,
+// 2.64 with two, 2.51 with four chunks of 262,144 frames in flight; more or smaller chunks do
+// not help).
 constexpr int kMaxPipes = 8;
 struct Pipes {
   int dev = -1;
@@ -1013,6 +1505,7 @@ struct Pipes {
     int d = 0;
     if (cudaGetDevice(&d) != cudaSuccess) return PP_E_CUDA;
     if (fork && d == dev) return PP_OK;
+    release();  // (streams and events of another device: the thread moved on)
     for (int i = 0; i < kMaxPipes; i++)
       if (cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) != cudaSuccess ||
           cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess)
@@ -1020,6 +1513,18 @@ struct Pipes {
     if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return PP_E_CUDA;
     dev = d;
     return PP_OK;
+  }
+  void release() {
+    for (int i = 0; i < kMaxPipes; i++) {
+      if (done[i]) cudaEventDestroy(done[i]);
+      if (st[i]) cudaStreamDestroy(st[i]);
+      done[i] = nullptr;
+      st[i] = nullptr;
+    }
+    if (fork) cudaEventDestroy(fork);
+    fork = nullptr;
+    dev = -1;
+    cudaGetLastError();
   }
 };
 thread_local Pipes t_pipes;
@@ -1035,40 +1540,43 @@ int env_int(const char *name, int dflt, int lo, int hi) {
 // the caller's stream around every kernel of the pipeline.
 constexpr int kPhases = 5;  // prep, cars, decide, emit, slow
 constexpr int kMaxTimedChunks = 4096;
-bool g_phase_timing = false;
+std::atomic<bool> g_phase_timing{false};
 struct PhaseEvents {
   cudaEvent_t ev[kPhases + 1];
 };
+std::mutex g_phase_mu;                    // guards the two vectors (callers plan from any thread)
 std::vector<PhaseEvents> g_phase_events;  // one entry per chunk launched since the last read
 std::vector<PhaseEvents> g_phase_pool;    // recycled events
 
-void phase_mark(PhaseEvents *pe, int i, cudaStream_t st) {
+void phase_mark(const PhaseEvents *pe, int i, cudaStream_t st) {
   if (pe) cudaEventRecord(pe->ev[i], st);
 }
-PhaseEvents *phase_begin() {
-  if (!g_phase_timing || (int)g_phase_events.size() >= kMaxTimedChunks) return nullptr;
-  PhaseEvents pe;
+// (returns a copy: the vector may grow under another thread's chunk)
+bool phase_begin(PhaseEvents &pe) {
+  if (!g_phase_timing.load(std::memory_order_relaxed)) return false;
+  std::lock_guard<std::mutex> lk(g_phase_mu);
+  if ((int)g_phase_events.size() >= kMaxTimedChunks) return false;
   if (!g_phase_pool.empty()) {
     pe = g_phase_pool.back();
     g_phase_pool.pop_back();
   } else {
     for (int i = 0; i <= kPhases; i++)
-      if (cudaEventCreate(&pe.ev[i]) != cudaSuccess) return nullptr;
+      if (cudaEventCreate(&pe.ev[i]) != cudaSuccess) return false;
   }
   g_phase_events.push_back(pe);
-  return &g_phase_events.back();
+  return true;
 }
 
 int sm_count() {
-  if (g_sm_count == 0) {
+  int n = g_sm_count.load(std::memory_order_relaxed);
+  if (n == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       n = 148;
-    g_sm_count = n;
+    g_sm_count.store(n, std::memory_order_relaxed);
   }
-  return g_sm_count;
+  return n;
 }
 
 int check_launch(const char *what) {
@@ -1093,6 +1601,49 @@ int grid_for(int64_t items, int blocks_per_sm) {
   return (int)(want < cap ? want : cap);
 }
 
+// Tile geometry of k_cars_t for `mc` car slots per frame (see CarsGeom).
+CarsGeom cars_geom(int mc, const pp_frames &in, int max_items) {
+  CarsGeom g;
+  const int c1 = mc > 0 ? mc : 1;
+  int F = max_items / c1;
+  F = F < 1 ? 1 : (F > 32 ? 32 : F);
+  if (((F * mc) & 1) && F > 1) F--;  // an even number of car slots per tile: 16-byte granules
+  g.F = F;
+  int G = 1;
+  while (G * 2 * F <= 32 && G * 2 <= c1) G *= 2;
+  g.G = G;
+  g.T = (F * mc + 1) & ~1;
+  if (g.T < 2) g.T = 2;
+  g.Cg = (c1 + G - 1) / G * G;
+  g.warp_bytes = cars_warp_bytes(g.T, g.F);
+  g.magic = (65536u + (unsigned)c1 - 1u) / (unsigned)c1;
+  g.bulk = mc > 0 && aligned16(in.car_x) && aligned16(in.car_y) && aligned16(in.car_vx) &&
+           aligned16(in.car_vy) && ((F * mc) % 2 == 0);
+  return g;
+}
+
+template <int kThreads>
+int launch_cars(const pp_map *map, const pp_config &cfg, const pp_frames &fin, const pp_plans &fout,
+                const Scratch &sc, int64_t cnt, const CarsGeom &g, size_t smem_map,
+                cudaStream_t st) {
+  const size_t smem = smem_map + (size_t)(kThreads / 32) * g.warp_bytes;
+  // (the opt-in limit is per function and device; raised whenever a call needs more)
+  static std::atomic<size_t> granted[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || granted[dev].load(std::memory_order_relaxed) < smem) {
+    if (cudaFuncSetAttribute(k_cars_t<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+      return check_launch("cudaFuncSetAttribute(k_cars_t)");
+    if (dev >= 0 && dev < 64) granted[dev].store(smem, std::memory_order_relaxed);
+  }
+  const int64_t n_tiles = (cnt + g.F - 1) / g.F;
+  const int64_t want = (n_tiles + kThreads / 32 - 1) / (kThreads / 32);
+  const int grid = (int)(want < sm_count() ? want : sm_count());
+  k_cars_t<kThreads><<<grid, kThreads, smem, st>>>(map->dev_table, map->n, cfg, fin, fout, sc, cnt, g);
+  return PP_OK;
+}
+
 using ppi::offset_frames;
 using ppi::offset_plans;
 
@@ -1112,7 +1663,7 @@ int ensure_smem(K kernel, size_t smem) {
 }  // namespace
 
 extern "C" int pp_set_kernel_variant(int variant) {
-  if (variant < 0 || variant > 2) return PP_E_ARG;
+  if (variant < 0 || variant > 3) return PP_E_ARG;
   g_variant = variant;
   return PP_OK;
 }
@@ -1130,20 +1681,23 @@ static int64_t chunk_for(int64_t n, int pipes) {
   if (c > cap) c = cap;
   return c < n ? c : n;
 }
-static int g_pipes_override = 0;  // pp_set_pipes
+static std::atomic<int> g_pipes_override{0};  // pp_set_pipes
 static int pipe_count() {
   static const int v = env_int("PP_PIPES", 4, 1, kMaxPipes);
-  return g_pipes_override > 0 ? g_pipes_override : v;
+  const int o = g_pipes_override.load(std::memory_order_relaxed);
+  return o > 0 ? o : v;
 }
 
 // Bytes of scratch the pipeline needs for a batch (0 for batches the fused kernel takes).
 // (a caller that brings its own scratch drives its own concurrency: one chunk in flight)
 size_t ppi::plan_scratch_bytes(int64_t n_frames, int max_cars) {
-  if (n_frames <= 0 || g_variant == 1 || (g_variant == 0 && n_frames < kFusedBelow)) return 0;
+  const int variant = g_variant.load(std::memory_order_relaxed);
+  if (n_frames <= 0 || variant == 1 || (variant == 0 && n_frames < kFusedBelow)) return 0;
   const int64_t chunk = chunk_for(n_frames, 1);
   const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
   const int n_buf = 1;
-  const size_t scratch = (scratch_bytes(chunk, max_cars) + 255) & ~(size_t)255;
+  const size_t scratch =
+      ((variant == 3 ? scratch3_bytes(chunk) : scratch_bytes(chunk, max_cars)) + 255) & ~(size_t)255;
   return n_buf * scratch + (size_t)n_frames * 2 * sizeof(int32_t) +
          (size_t)n_chunks * 2 * sizeof(int32_t) + 256;
 }
@@ -1170,14 +1724,12 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
                             const pp_plans *out, int64_t n_frames, void *cuda_stream,
                             char *caller_scratch, int64_t *stats_dev) {
   if (!map || !cfg || !in || !out || n_frames < 0) return PP_E_ARG;
+  int rc0;
   if (stats_dev &&
       cudaMemsetAsync(stats_dev, 0, PP_STATS_LEN * sizeof(int64_t), (cudaStream_t)cuda_stream) !=
           cudaSuccess)
     return check_launch("pp_plan_stats_batch memset");
-  if (!map->dev_table) {
-    ppi::set_cuda_error("pp_plan_batch: map has no device table (no usable CUDA device)", 0, "");
-    return PP_E_CUDA;  // there is no CPU planning path
-  }
+  if ((rc0 = ppi::check_map_device(map, "pp_plan_batch")) != PP_OK) return rc0;
   if (in->max_cars < 0 || in->max_cars > PP_MAX_CARS) return PP_E_RANGE;
   if (!in->ego_x || !in->ego_y || !in->ego_yaw_deg || !in->ego_speed_mph || !in->prev_n ||
       !in->prev_x || !in->prev_y || !in->target_lane_in || !in->n_cars)
@@ -1195,8 +1747,6 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
   if ((rc = ensure_smem(plan_fused, smem)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_prep, smem)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_cars, smem)) != PP_OK) return rc;
-  const size_t smem_decide = (size_t)PPD_SWEEP_ROWS * PPD_TAILK * kBlock * sizeof(double);
-  if ((rc = ensure_smem(k_decide, smem_decide)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_slow, smem)) != PP_OK) return rc;
   const size_t smem_emit = (size_t)5 * PPD_TAILK * kBlock * sizeof(double);
   if ((rc = ensure_smem(k_emit<ArrayOut, false>, smem_emit)) != PP_OK) return rc;
@@ -1204,8 +1754,19 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
   if ((rc = ensure_smem(k_emit<ArrayOut, true>, smem_emit)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_emit<PairOut, true>, smem_emit)) != PP_OK) return rc;
   const bool paired = (((uintptr_t)out->next_x | (uintptr_t)out->next_y) & 15) == 0;
+  const int variant = g_variant.load(std::memory_order_relaxed);  // one reading per call
+  const bool tiled = variant == 3;  // k_cars_t + reduced Behav in the scratch
+  const size_t smem_tile =
+      (size_t)(5 * PPD_TAILK * kBlock + 2 * kBlock * PP_PREV_KEEP) * sizeof(double);
+  static_assert(PPD_SWEEP_ROWS == 5, "k_decide_t tile size");
+  if ((rc = ensure_smem(k_decide_t<false>, smem_tile)) != PP_OK) return rc;
+  if ((rc = ensure_smem(k_decide_t<true>, smem_tile)) != PP_OK) return rc;
+  if ((rc = ensure_smem(k_slow_t, smem)) != PP_OK) return rc;
+  static const int decide_bulk_out = env_int("PP_DECIDE_BULK_OUT", 1, 0, 1);  // experiments
+  static const int decide_blocks = env_int("PP_DECIDE_BLOCKS", 4, 1, 16);
+  const int bulk_prev = aligned16(in->prev_x) && aligned16(in->prev_y);
 
-  const bool fused = g_variant == 1 || (g_variant == 0 && n_frames < kFusedBelow);
+  const bool fused = variant == 1 || (variant == 0 && n_frames < kFusedBelow);
   if (fused) {
     plan_fused<<<grid_for(n_frames, 8), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, *in, *out,
                                                             n_frames);
@@ -1249,7 +1810,8 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     lane_side[k] = &side_for(lane_st[k]);
     if ((rc = lane_side[k]->ensure()) != PP_OK) return rc;
   }
-  const size_t scratch = (scratch_bytes(chunk, mc) + 255) & ~(size_t)255;
+  const size_t scratch =
+      ((tiled ? scratch3_bytes(chunk) : scratch_bytes(chunk, mc)) + 255) & ~(size_t)255;
   const size_t queues = (size_t)n_frames * 2 * sizeof(int32_t);
   const size_t counters = (size_t)n_chunks * 2 * sizeof(int32_t);
   char *buf = caller_scratch;
@@ -1262,7 +1824,18 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     }
   }
   Scratch scs[kMaxPipes];
-  for (int k = 0; k < pipes; k++) scs[k] = carve_scratch(buf + k * scratch, chunk, mc);
+  for (int k = 0; k < pipes; k++)
+    scs[k] = tiled ? carve_scratch3(buf + k * scratch, chunk) : carve_scratch(buf + k * scratch, chunk, mc);
+  static const int cars_items = env_int("PP_CARS_ITEMS", 256, 32, 256);
+  static const int cars_threads = env_int("PP_CARS_THREADS", 0, 0, 1024);
+  const CarsGeom cg = cars_geom(mc, *in, cars_items);
+  // as many warps per SM as the shared memory holds (one block per SM)
+  int cthreads = cars_threads;
+  if (cthreads == 0) {
+    const size_t room = 227 * 1024 - 1024 - smem;
+    const int w = (int)(room / (size_t)cg.warp_bytes);
+    cthreads = w >= 24 ? 768 : (w >= 20 ? 640 : (w >= 16 ? 512 : (w >= 12 ? 384 : 256)));
+  }
   int32_t *q_base = (int32_t *)(buf + pipes * scratch);
   int32_t *n_base = (int32_t *)(buf + pipes * scratch + queues);
   cudaMemsetAsync(n_base, 0, counters + 64, st);
@@ -1274,7 +1847,8 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
   rc = PP_OK;
   const int side_grid = sm_count() * 4;
   int64_t ci = 0;
-  PhaseEvents *pe = nullptr;
+  PhaseEvents pe_store;
+  const PhaseEvents *pe = nullptr;
   for (int64_t lo = 0; lo < n_frames && rc == PP_OK; lo += chunk, ci++) {
     const int64_t cnt = (n_frames - lo) < chunk ? (n_frames - lo) : chunk;
     const pp_frames fin = offset_frames(*in, lo);
@@ -1291,16 +1865,69 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     sc.xsum = stats_dev ? (unsigned long long *)stats_dev + PP_STAT_XSUM : nullptr;
     // the side stream may still be reading this pipe's scratch for its previous chunk
     if (ci >= pipes) cudaStreamWaitEvent(ls, side.ev_done, 0);
-    pe = phase_begin();
+    pe = phase_begin(pe_store) ? &pe_store : nullptr;
     phase_mark(pe, 0, ls);
+    if (tiled) {
+      // (the car arrays of a chunk start on a 16-byte boundary when those of the batch do:
+      // chunks are multiples of 1024 frames)
+      k_prep<<<grid_for(cnt, 12), kBlock, smem, ls>>>(map->dev_table, map->n, *cfg, fin, sc, cnt);
+      phase_mark(pe, 1, ls);
+      if (mc > 0) {
+        switch (cthreads) {
+          case 768: rc = launch_cars<768>(map, *cfg, fin, fout, sc, cnt, cg, smem, ls); break;
+          case 640: rc = launch_cars<640>(map, *cfg, fin, fout, sc, cnt, cg, smem, ls); break;
+          case 512: rc = launch_cars<512>(map, *cfg, fin, fout, sc, cnt, cg, smem, ls); break;
+          case 384: rc = launch_cars<384>(map, *cfg, fin, fout, sc, cnt, cg, smem, ls); break;
+          default: rc = launch_cars<256>(map, *cfg, fin, fout, sc, cnt, cg, smem, ls); break;
+        }
+        if (rc != PP_OK) break;
+      }
+      phase_mark(pe, 2, ls);
+      k_decide_t<true><<<grid_for(cnt, decide_blocks), kBlock, smem_tile, ls>>>(
+          map->dev_table, map->n, *cfg, fin, fout, sc, cnt, bulk_prev,
+          paired && decide_bulk_out ? 1 : 0);
+      phase_mark(pe, 3, ls);
+      cudaEventRecord(side.ev_a, ls);
+      cudaStreamWaitEvent(side.st, side.ev_a, 0);
+      k_fallback<<<side_grid, kBlock, 0, side.st>>>(fout, sc, sc.slow_qa, sc.slow_na);
+      const int eg = grid_for(cnt, 12);
+      if (paired) {
+        if (sc.xsum)
+          k_emit<PairOut, true><<<eg, kBlock, smem_emit, ls>>>(*cfg, fout, sc, cnt);
+        else
+          k_emit<PairOut, false><<<eg, kBlock, smem_emit, ls>>>(*cfg, fout, sc, cnt);
+      } else {
+        if (sc.xsum)
+          k_emit<ArrayOut, true><<<eg, kBlock, smem_emit, ls>>>(*cfg, fout, sc, cnt);
+        else
+          k_emit<ArrayOut, false><<<eg, kBlock, smem_emit, ls>>>(*cfg, fout, sc, cnt);
+      }
+      phase_mark(pe, 4, ls);
+      cudaEventRecord(side.ev_b, ls);
+      cudaStreamWaitEvent(side.st, side.ev_b, 0);
+      k_slow_t<<<side_grid, kBlock, smem, side.st>>>(map->dev_table, map->n, *cfg, fin, fout, sc.xsum,
+                                                     sc.slow_qb, sc.slow_nb);
+      cudaEventRecord(side.ev_done, side.st);
+      ppi::count_launch(mc > 0 ? 6 : 5);
+      if (stats_dev) {
+        cudaStreamWaitEvent(ls, side.ev_done, 0);
+        stats_kernel<<<stats_grid(cnt), 256, 0, ls>>>(fout, cnt, (unsigned long long *)stats_dev,
+                                                      false);
+        ppi::count_launch();
+      }
+      rc = check_launch("plan pipeline (tiled)");
+      phase_mark(pe, 5, ls);
+      continue;
+    }
     k_prep<<<grid_for(cnt, 12), kBlock, smem, ls>>>(map->dev_table, map->n, *cfg, fin, sc, cnt);
     phase_mark(pe, 1, ls);
     if (mc > 0)
       k_cars<<<grid_for((cnt * mc + kTileK - 1) / kTileK, 12), kBlock, smem, ls>>>(
           map->dev_table, map->n, fin, fout, sc, cnt);
     phase_mark(pe, 2, ls);
-    k_decide<<<grid_for(cnt, 12), kBlock, smem_decide, ls>>>(map->dev_table, map->n, *cfg, fin, fout,
-                                                             sc, cnt);
+    k_decide_t<false><<<grid_for(cnt, decide_blocks), kBlock, smem_tile, ls>>>(
+        map->dev_table, map->n, *cfg, fin, fout, sc, cnt, bulk_prev,
+        paired && decide_bulk_out ? 1 : 0);
     phase_mark(pe, 3, ls);
     // side stream: the frames k_decide queued, concurrently with k_emit and the next chunk
     cudaEventRecord(side.ev_a, ls);
@@ -1380,6 +2007,7 @@ extern "C" int pp_get_phase_ms(double *ms_out, int64_t *chunks_out) {
   if (!ms_out) return PP_E_ARG;
   for (int i = 0; i < kPhases; i++) ms_out[i] = 0;
   int rc = PP_OK;
+  std::lock_guard<std::mutex> lk(g_phase_mu);
   for (PhaseEvents &pe : g_phase_events) {
     if (cudaEventSynchronize(pe.ev[kPhases]) != cudaSuccess) rc = PP_E_CUDA;
     for (int i = 0; i < kPhases && rc == PP_OK; i++) {

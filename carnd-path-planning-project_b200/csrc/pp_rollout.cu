@@ -281,9 +281,9 @@ extern "C" int pp_rollouts_create(const pp_map *map, int64_t n, int32_t c, uint6
   if (!out) return PP_E_ARG;
   *out = nullptr;
   if (!map || n <= 0 || c < 0 || c > PP_MAX_CARS) return PP_E_ARG;
-  if (!map->dev_table) {
-    ppi::set_cuda_error("pp_rollouts_create: map has no device table (no usable CUDA device)", 0, "");
-    return PP_E_CUDA;
+  {
+    const int rc = ppi::check_map_device(map, "pp_rollouts_create");
+    if (rc != PP_OK) return rc;
   }
   pp_rollouts *r = new (std::nothrow) pp_rollouts();
   if (!r) return PP_E_NOMEM;
@@ -542,6 +542,10 @@ extern "C" int pp_rollouts_run(pp_rollouts *r, const pp_config *cfg, int64_t n_t
     return PP_E_ARG;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   if (n_ticks == 0) return PP_OK;
+  {
+    const int rc = ppi::check_map_device(r->map, "pp_rollouts_run");
+    if (rc != PP_OK) return rc;
+  }
   // A tick is ~36 short launches over 8 streams (4 groups, each with its side stream).  It can
   // be captured once and replayed as a CUDA graph (PP_ROLLOUT_GRAPH=1; the pipeline's scratch is
   // owned by the rollouts object, so the graph holds only kernels, memsets and event edges).

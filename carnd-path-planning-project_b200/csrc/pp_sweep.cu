@@ -261,9 +261,9 @@ extern "C" int pp_sweep_batch(const pp_map *map, const pp_config *cfg, const pp_
   if (!map || !cfg || !in || !out || n < 0) return PP_E_ARG;
   if (!out->best || !out->best_score || !out->next_x || !out->next_y || !out->n_points)
     return PP_E_ARG;
-  if (!map->dev_table) {
-    ppi::set_cuda_error("pp_sweep_batch: map has no device table (no usable CUDA device)", 0, "");
-    return PP_E_CUDA;
+  {
+    const int rc = ppi::check_map_device(map, "pp_sweep_batch");
+    if (rc != PP_OK) return rc;
   }
   if (n == 0) return PP_OK;
   cudaStream_t st = (cudaStream_t)cuda_stream;

@@ -319,11 +319,8 @@ int finish(const char *what) {
 inline int grid_for(int64_t n) { return (int)((n + kB - 1) / kB); }
 inline size_t map_smem(const pp_map *m) { return map_stage_bytes(m->n); }
 int need_map(const pp_map *m, const char *who) {
-  if (!m) return PP_E_ARG;
-  if (!m->dev_table) {
-    ppi::set_cuda_error(who, 0, "map has no device table (no usable CUDA device)");
-    return PP_E_CUDA;
-  }
+  const int rc = ppi::check_map_device(m, who);
+  if (rc != PP_OK) return rc;
   if (map_smem(m) > 48 * 1024) return PP_E_RANGE;
   return PP_OK;
 }

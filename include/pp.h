@@ -19,7 +19,8 @@
  *   - "dev" pointers are CUDA device pointers on the device that was current
  *     when the pp_map was created; "host" pointers are ordinary (ideally
  *     pinned) host memory.  The caller owns every buffer; the library owns
- *     pp_map.
+ *     pp_map.  A call made while another device is current fails with
+ *     PP_E_ARG (one pp_map per device).
  *   - pp_plan_batch is asynchronous on the caller's stream and re-entrant:
  *     the reference keeps reference_waypoint_id/ratio as mutable state on
  *     the shared Map (src/main.cpp:132-133); here that state lives in
@@ -162,6 +163,11 @@ typedef struct pp_plans {
 #define PP_STATS_LEN (PP_STAT_XSUM + 1)
 
 int pp_version(void);
+/* Optional, before the process's first CUDA call: asks for 32 hardware work queues
+ * (CUDA_DEVICE_MAX_CONNECTIONS, unless the environment already sets it).  The planner keeps up
+ * to nine streams busy; with the default 8 queues independent streams share a queue and
+ * serialise.  The library never changes the environment by itself. */
+int pp_init(void);
 const char *pp_strerror(int code);
 const char *pp_last_cuda_error(void);
 int pp_device_count(void); /* number of CUDA devices, or PP_E_CUDA */
@@ -204,8 +210,9 @@ int pp_plan_stats_batch(const pp_map *map, const pp_config *cfg, const pp_frames
                         const pp_plans *out, int64_t n_frames, int64_t *stats_dev,
                         void *cuda_stream);
 
-/* Kernel selection for pp_plan_batch: 0 = auto (pipeline; the fused kernel for
- * batches under 4096 frames), 1 = fused single kernel, 2 = pipeline. */
+/* Kernel selection for pp_plan_batch: 0 = auto (tiled pipeline; the fused kernel for
+ * batches under 4096 frames), 1 = fused single kernel, 2 = strided pipeline (round 1),
+ * 3 = tiled pipeline (frame tiles through shared memory by TMA bulk copies). */
 int pp_set_kernel_variant(int variant);
 /* Chunks of a large batch that pp_plan_batch keeps in flight at once on internal streams:
  * 1..8, 0 = default (4).  1 runs the kernels of the pipeline strictly one after the other,

@@ -79,19 +79,86 @@ def test_gpu_vs_reference_binary(pp, torch_cuda, gmap):
 
 
 def test_fused_and_pipeline_variants_are_bitwise_identical(pp, torch_cuda, gmap):
-    """The single fused kernel (variant 1) and the three-phase pipeline (variant 2)
-    run the same __device__ code with different thread mappings: every output
-    bit must agree."""
+    """The single fused kernel (variant 1), the strided pipeline (variant 2) and the tiled
+    pipeline (variant 3, the default for large batches) run the same __device__ code with
+    different thread mappings: every output bit must agree."""
     fb = pp.synth_frames(gmap, 300000, 12, seed=61, rare_permille=100)  # > 1 pipeline chunk
     try:
         pp.set_kernel_variant(1)
         a = gpu_plan(pp, torch_cuda, gmap, fb)
         pp.set_kernel_variant(2)
         b = gpu_plan(pp, torch_cuda, gmap, fb)
+        pp.set_kernel_variant(3)
+        c = gpu_plan(pp, torch_cuda, gmap, fb)
     finally:
         pp.set_kernel_variant(0)
     for k in a.fields:
         assert np.array_equal(getattr(a, k), getattr(b, k), equal_nan=True), k
+        assert np.array_equal(getattr(a, k), getattr(c, k), equal_nan=True), k
+
+
+@pytest.mark.parametrize("cars,n", [(0, 4500), (1, 5003), (2, 4097), (5, 4999), (12, 6001),
+                                    (20, 4100), (33, 4101), (63, 4200), (64, 4203)])
+def test_pipeline_tile_geometries(pp, torch_cuda, gmap, oracle, cars, n):
+    """Every tile geometry of the tiled pipeline (frames per warp tile, lanes per frame in the
+    reduction, odd car counts that cannot be bulk-copied, ragged last tiles) and the strided
+    pipeline at the same sizes (max_cars = 1 once divided by zero there): bit for bit against
+    the fused kernel, and against the oracle."""
+    rng = np.random.default_rng(cars)
+    fb = pp.synth_frames(gmap, n, cars, seed=300 + cars, rare_permille=100, max_cars=max(cars, 1))
+    if cars > 1:
+        fb.n_cars[::3] = rng.integers(0, cars + 1, len(fb.n_cars[::3]))
+    try:
+        pp.set_kernel_variant(1)
+        a = gpu_plan(pp, torch_cuda, gmap, fb)
+        pp.set_kernel_variant(2)
+        b = gpu_plan(pp, torch_cuda, gmap, fb)
+        pp.set_kernel_variant(3)
+        c = gpu_plan(pp, torch_cuda, gmap, fb)
+    finally:
+        pp.set_kernel_variant(0)
+    for k in a.fields:
+        if k.startswith("car_"):  # slots at and beyond n_cars are not written
+            live = np.arange(fb.max_cars)[None, :] < np.minimum(fb.n_cars, fb.max_cars)[:, None]
+            x, y, z = getattr(a, k)[live], getattr(b, k)[live], getattr(c, k)[live]
+        else:
+            x, y, z = getattr(a, k), getattr(b, k), getattr(c, k)
+        assert np.array_equal(x, y, equal_nan=True), ("strided", k)
+        assert np.array_equal(x, z, equal_nan=True), ("tiled", k)
+    sub = fb.slice(0, 1500)
+    want = oracle.plan(sub, threads=8)
+    got = {k: getattr(c, k)[:1500] for k in c.fields}
+    assert_plans_equal(got, plans_dict(want), ALL_FLAGS, bitwise_traj=False)
+
+
+def test_unaligned_buffers_take_the_plain_copies(pp, torch_cuda, gmap):
+    """Frame and plan arrays that start 8 bytes off a 16-byte boundary cannot be moved by TMA
+    bulk copies: the kernels fall back to ordinary loads / stores, with identical results."""
+    torch = torch_cuda
+    n = 5000
+    fb = pp.synth_frames(gmap, n, 12, seed=71, rare_permille=100)
+    want = gpu_plan(pp, torch, gmap, fb, cars=False)
+    df = pp.DeviceFrames(fb)
+    for k, v in list(df.t.items()):  # same values, every array shifted by one element
+        big = torch.empty(v.numel() + 4, dtype=v.dtype, device=v.device)
+        off = 1 if v.element_size() == 8 else 2
+        big[off:off + v.numel()] = v.reshape(-1)
+        df.t[k] = big[off:off + v.numel()].view(v.shape)
+        assert df.t[k].data_ptr() % 16 == 8
+    dp = pp.DevicePlans(n, 12, diag=True, cars=False)
+    for k, v in list(dp.t.items()):
+        big = torch.zeros(v.numel() + 4, dtype=v.dtype, device=v.device)
+        off = 1 if v.element_size() == 8 else 2
+        dp.t[k] = big[off:off + v.numel()].view(v.shape)
+    try:
+        pp.set_kernel_variant(3)
+        pp.plan_batch(gmap, df, dp)
+        torch.cuda.synchronize()
+    finally:
+        pp.set_kernel_variant(0)
+    got = dp.to_host()
+    for k in want.fields:
+        assert np.array_equal(getattr(got, k), getattr(want, k), equal_nan=True), k
 
 
 def test_ragged_and_edge_inputs(pp, torch_cuda, gmap, oracle):
