@@ -91,12 +91,15 @@ def cpu_checker():
     return checkers.Checker("oracle"), "port"
 
 
-def time_cpu(pp, m, n_frames, passes=1, cars=N_CARS):
-    """Reference CPU implementation of the path on all host threads."""
+def time_cpu(pp, m, n_frames, passes=1, cars=N_CARS, bufs=None):
+    """Reference CPU implementation of the path on all host threads.  bufs: (frames, plans) to
+    reuse between calls."""
     chk, kind = cpu_checker()
     threads = cpu_threads()
-    frames = pp.synth_frames(m, n_frames, cars, seed=SEED)
-    plans = pp.PlanBatch(n_frames, cars, diag=True, cars=False)
+    if bufs is None:
+        bufs = (pp.synth_frames(m, n_frames, cars, seed=SEED),
+                pp.PlanBatch(n_frames, max(cars, 1), diag=True, cars=False))
+    frames, plans = bufs
     best = float("inf")
     for _ in range(passes):
         t0 = time.perf_counter()
@@ -113,11 +116,13 @@ def run_reference(args):
     from __graft_entry__ import load_package
     pp = load_package()
     m = pp.Map()
-    n = 1 << 18  # bounded sample of the workload per step
+    n = args.frames or FRAMES_PER_GPU  # the same frames per step as the repo arm
+    bufs = (pp.synth_frames(m, n, args.cars, seed=SEED),
+            pp.PlanBatch(n, max(args.cars, 1), diag=True, cars=False))
     total_t, total_f = 0.0, 0
     kind, threads = None, None
     for i in range(args.warmup + args.steps):
-        fps, t, kind, threads = time_cpu(pp, m, n, cars=args.cars)
+        fps, t, kind, threads = time_cpu(pp, m, n, cars=args.cars, bufs=bufs)
         if i >= args.warmup:
             total_t += t
             total_f += n
@@ -127,7 +132,10 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total_t / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"first {n} frames of the workload per step"},
+        "config": {"workload": WORKLOAD if n == FRAMES_PER_GPU and args.cars == N_CARS else
+                   f"{n} independent synthetic frames x {args.cars} cars x 3 lanes",
+                   "frames_per_gpu": n, "cars_per_frame": args.cars,
+                   "sample": f"all {n} frames of the workload per step"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind,
                          "sample": f"{n} frames per step, {threads} threads, "
                                    f"{'reference classes (oracle/_ref)' if kind == 'reference' else 'C restatement'}"},
@@ -252,7 +260,7 @@ def run_sweep(args):
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled every ~5 ms through NVML on a thread while the
+    """SM clock + throttle reasons sampled every ~2 ms through NVML on a thread while the
     timed region runs (nvidia-smi's own loop is too coarse for a sub-second region)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap"}
@@ -303,7 +311,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.002)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -318,26 +326,116 @@ class ClockSampler:
         return out
 
 
+def make_comm(pp, dist, rank, world):
+    """An ncclComm_t made through the C ABI (pp_comm_*); torch.distributed only carries rank 0's
+    128-byte id to the other ranks."""
+    def exchange(raw):
+        box = [raw if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+    return pp.Comm(rank, world, exchange if world > 1 else None)
+
+
+def single_rank_stats(pp, m, world, n, cars, first_of_rank, torch):
+    """The statistics of all ranks' shards planned on THIS device alone (the N-rank reduced
+    vector must equal it bit for bit): shards generated in HBM one after the other."""
+    tot_i = torch.zeros(pp.STATS_LEN, dtype=torch.int64, device="cuda")
+    tot_f = None
+    df = pp.DeviceFrames.empty(n, max(cars, 1))
+    dp = pp.DevicePlans(n, max(cars, 1), diag=True, cars=False)
+    for r in range(world):
+        pp.synth_frames_dev(m, n, cars, seed=SEED, first_frame=first_of_rank(r), out=df)
+        st = pp.plan_stats_batch(m, df, dp)
+        fs = pp.fstats_batch(dp)
+        tot_i += st
+        if tot_f is None:
+            tot_f = fs.clone()
+        else:
+            tot_f[:pp.FSTAT_NMIN] = torch.minimum(tot_f[:pp.FSTAT_NMIN], fs[:pp.FSTAT_NMIN])
+            tot_f[pp.FSTAT_NMIN:] = torch.maximum(tot_f[pp.FSTAT_NMIN:], fs[pp.FSTAT_NMIN:])
+    torch.cuda.synchronize()
+    return tot_i, tot_f
+
+
+def traffic_for(cars):
+    """ncu dram__bytes_read+write of the pipeline's kernels, from the committed capture of THIS
+    car count (profiles/traffic.json, profiles/traffic_c64.json); None when there is none."""
+    name = "traffic.json" if cars == N_CARS else f"traffic_c{cars}.json"
+    prof = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(prof):
+        return None, {}, None, None
+    try:
+        tj = json.load(open(prof))
+        if int(tj.get("cars_per_frame", N_CARS)) != cars:
+            return None, {}, None, None
+        by_kernel = tj.get("dram_bytes_per_launch", {})
+        per_frame = sum(by_kernel.values()) / float(tj["frames_per_launch"])
+        view = {k: tj.get(k) for k in ("fp64_pipe_active_pct", "issue_active_pct",
+                                       "active_lanes_per_warp_instr")}
+        return per_frame, by_kernel, view, tj.get("source")
+    except Exception:
+        return None, {}, None, None
+
+
+def cpu_baseline_legs(pp, m, n, cars):
+    """the reference's own classes on all host threads (the figure of record),
+    on one thread, and once with the reference's own build flags (no -O) — the last two on
+    bounded samples."""
+    import checkers
+    fps, secs, kind, threads = time_cpu(pp, m, n, cars=cars)
+    out = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+           "sample": f"{n} frames of the workload, 1 pass, {threads} threads ({secs:.1f} s wall)"}
+    small = min(n, 1 << 16)
+    frames = pp.synth_frames(m, small, cars, seed=SEED)
+    plans = pp.PlanBatch(small, max(cars, 1), diag=True, cars=False)
+    chk, _ = cpu_checker()
+    t0 = time.perf_counter()
+    chk.plan_into(frames, plans, threads=1, want_flags=False)
+    out["one_thread"] = {"value": small / (time.perf_counter() - t0), "unit": "frames/s",
+                         "cores": 1, "sample": f"first {small} frames, 1 thread, -O2"}
+    if checkers.available("ref_O0"):
+        slow = checkers.Checker("ref_O0")
+        tiny = min(small, 1 << 14)
+        fr = frames.slice(0, tiny)
+        pl = pp.PlanBatch(tiny, max(cars, 1), diag=True, cars=False)
+        t0 = time.perf_counter()
+        slow.plan_into(fr, pl, threads=1, want_flags=False)
+        out["reference_flags_no_O"] = {
+            "value": tiny / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1,
+            "sample": f"first {tiny} frames, 1 thread, the reference's own flags (-std=c++11, no -O)"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU")
+    ap.add_argument("--frames", type=int, default=None,
+                    help="frames per GPU (weak scaling) / in total (strong scaling)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-check", action="store_true",
+                    help="skip the N-rank == 1-rank statistics check (N > 1)")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--cars", type=int, default=N_CARS,
                     help="cars per frame (12 = configs[1], the headline; 64 = configs[4])")
-    ap.add_argument("--workload", default="frames", choices=["frames", "rollouts", "sweep"],
-                    help="frames = BASELINE configs[1] (the headline metric, default); "
-                         "rollouts = configs[2], closed-loop rollouts (secondary line)")
+    ap.add_argument("--workload", default="frames",
+                    choices=["frames", "dense64", "rollouts", "sweep"],
+                    help="frames = BASELINE configs[1] (the headline metric, default); dense64 = "
+                         "configs[4], 64M frames x 64 cars in total, generated in HBM and sharded; "
+                         "rollouts = configs[2]; sweep = configs[3] (secondary lines)")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="weak: --frames per GPU (default for frames); strong: --frames in total, "
+                         "split over the GPUs (default for dense64)")
     ap.add_argument("--rollouts", type=int, default=65536, help="rollouts per GPU")
     ap.add_argument("--ticks", type=int, default=1000)
     ap.add_argument("--consume-k", type=int, default=1)
     args = ap.parse_args()
     quiet_stdout()
+    if args.workload in ("rollouts", "sweep") and args.frames is None:
+        args.frames = FRAMES_PER_GPU
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "rollouts":
@@ -361,23 +459,52 @@ def main():
     pp = load_package()
     pp.set_kernel_variant(args.variant)
 
-    n = args.frames
-    m = pp.Map()
-    frames = pp.synth_frames(m, n, args.cars, seed=SEED, first_frame=rank * n)
-    df = pp.DeviceFrames(frames)
-    dp = pp.DevicePlans(n, args.cars, diag=True, cars=False)
-    stream = torch.cuda.current_stream()
+    dense = args.workload == "dense64"
+    cars = 64 if dense else args.cars
+    scaling = args.scaling or ("strong" if dense else "weak")
+    if dense:
+        total = args.frames or (64 << 20)
+        cap = 32 << 20  # frames x 64 cars one B200 holds with its plans (108 GB)
+        if scaling == "strong":
+            n = min(total // world, cap)
+        else:
+            n = min(total, cap)
+        if args.steps == 50:
+            args.steps = 3
+        workload = (f"configs[4]: {total} frames x 64 cars in total, generated in HBM "
+                    f"(pp_synth_frames_dev), {n} frames resident per GPU"
+                    + (" (the largest single-GPU slice)" if n * world < total else ""))
+    else:
+        per = args.frames or FRAMES_PER_GPU
+        n = per // world if scaling == "strong" else per
+        total = n * world
+        workload = (WORKLOAD if cars == N_CARS and n == FRAMES_PER_GPU else
+                    f"{n} independent synthetic frames x {cars} cars x 3 lanes per GPU")
+    first_of_rank = lambda r: r * n  # noqa: E731  contiguous shards of one global stream
+    mc = max(cars, 1)
 
-    import torch as _t
-    st_buf = _t.empty(pp.STATS_LEN, dtype=_t.int64, device="cuda")
+    m = pp.Map()
+    if dense:
+        frames = None
+        df = pp.synth_frames_dev(m, n, cars, seed=SEED, first_frame=first_of_rank(rank))
+    else:
+        frames = pp.synth_frames(m, n, cars, seed=SEED, first_frame=first_of_rank(rank))
+        df = pp.DeviceFrames(frames)
+    dp = pp.DevicePlans(n, mc, diag=True, cars=False)
+    stream = torch.cuda.current_stream()
+    comm = make_comm(pp, dist, rank, world)
+    st_buf = torch.empty(pp.STATS_LEN, dtype=torch.int64, device="cuda")
+    fs_buf = torch.empty(pp.FSTATS_LEN, dtype=torch.float64, device="cuda")
 
     def step():
         # plan + aggregate statistics in one call (pp_plan_stats_batch == pp_plan_batch followed
         # by pp_stats_batch; a chunk's statistics overlap the planning of the other chunks)
-        st = pp.plan_stats_batch(m, df, dp, out=st_buf)
-        if world > 1:
-            dist.all_reduce(st)  # ncclSum of the int64 statistics vector
-        return st
+        return pp.plan_stats_batch(m, df, dp, out=st_buf)
+
+    def final_reduce():
+        # the f64 minima / maxima of the last plans, then the ONE collective of the job
+        pp.fstats_batch(dp, out=fs_buf)
+        comm.stats_reduce(st_buf, fs_buf)
 
     def fence():
         torch.cuda.synchronize()
@@ -387,6 +514,7 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    final_reduce()
     fence()
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -397,23 +525,26 @@ def main():
     fence()
     ev0.record(stream)
     for i in range(args.steps):
-        st = step()
+        step()
+    final_reduce()
     ev1.record(stream)
     fence()
     launches = pp.launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
+    stats = st_buf.cpu().numpy().copy()
+    fstats = fs_buf.cpu().numpy().copy()
     # pp_plan_batch alone (the pipeline without the statistics pass), for the roofline
     for i in range(args.steps):
         k_start[i].record(stream)
         pp.plan_batch(m, df, dp)
         k_stop[i].record(stream)
     fence()
+    clocks = sampler.stop() if sampler else None  # (both loops above run the GPU flat out)
     # Per-kernel breakdown: in the timed region four chunks are in flight at once, so a kernel's
     # own duration cannot be read there.  A few extra (untimed) steps run the same launches
     # strictly one after the other with CUDA events around each kernel.
     pp.set_pipes(1)
     pp.set_phase_timing(True)
-    bd_steps = 3
+    bd_steps = 1 if dense else 3
     for _ in range(bd_steps):
         pp.plan_batch(m, df, dp)
     phase_ms, phase_chunks = pp.get_phase_ms()
@@ -427,16 +558,30 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, kern_ms = float(t[0]), float(t[1])
-    stats = st.cpu().numpy()
     value = world * n * args.steps / (total_ms * 1e-3)
 
+    # ---- the N-rank reduced statistics against a single-rank pass over the same frames ----
+    stats_check = None
+    if world > 1 and not args.no_check:
+        if rank == 0:
+            one_i, one_f = single_rank_stats(pp, m, world, n, cars, first_of_rank, torch)
+            assert np.array_equal(one_i.cpu().numpy(), stats), \
+                ("N-rank int64 statistics differ from the single-rank pass", stats, one_i)
+            assert np.array_equal(one_f.cpu().numpy(), fstats), \
+                ("N-rank f64 statistics differ from the single-rank pass", fstats, one_f)
+            stats_check = f"{world}-rank pp_stats_reduce == 1-rank pass over the same {world * n} frames (int64 and f64 vectors, bit for bit)"
+        dist.barrier()
+
     # ---- end to end through the host entry point (pinned host buffers) ----
-    hf = pp.FrameBatch(n, args.cars)
+    e2e_n = n if not dense else min(n, 1 << 20)
+    if frames is None:
+        frames = pp.synth_frames(m, e2e_n, cars, seed=SEED, first_frame=first_of_rank(rank))
+    hf = pp.FrameBatch(e2e_n, mc)
     for k, v in frames.arrays().items():
-        pinned = torch.from_numpy(v).pin_memory()
+        pinned = torch.from_numpy(v[:e2e_n]).pin_memory()
         setattr(hf, k, pinned.numpy())
         hf.__dict__.setdefault("_keep", []).append(pinned)
-    hp = pp.PlanBatch(n, args.cars, diag=True, cars=False)
+    hp = pp.PlanBatch(e2e_n, mc, diag=True, cars=False)
     for k in hp.fields:
         pinned = torch.from_numpy(getattr(hp, k)).pin_memory()
         setattr(hp, k, pinned.numpy())
@@ -452,36 +597,24 @@ def main():
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * n / float(te[0])
+    e2e_value = world * e2e_n / float(te[0])
 
     if rank == 0:
         peak, peak_src = peaks()
-        bytes_in = 204 + 36 * args.cars
+        bytes_in = 204 + 36 * cars
         alg_bytes = (bytes_in + BYTES_OUT) * n
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        # dram__bytes_read+write of the pipeline's kernels from the committed ncu capture
-        # (profiles/traffic.json: bytes per 262,144-frame launch, summed over the kernels)
-        traffic, traffic_by_kernel, ncu_view = None, {}, None
-        prof = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(prof):
-            try:
-                tj = json.load(open(prof))
-                traffic_by_kernel = tj.get("dram_bytes_per_launch", {})
-                per_frame = sum(traffic_by_kernel.values()) / float(tj["frames_per_launch"])
-                traffic = per_frame * n
-                # what actually bounds these kernels (ncu, each kernel alone)
-                ncu_view = {k: tj.get(k) for k in ("fp64_pipe_active_pct", "issue_active_pct",
-                                                   "active_lanes_per_warp_instr")}
-            except Exception:
-                traffic, traffic_by_kernel, ncu_view = None, {}, None
-        names = ["k_prep", "k_cars", "k_decide", "k_emit", "side-stream tail (k_fallback/k_slow join)"]
+        per_frame_traffic, traffic_by_kernel, ncu_view, traffic_src = traffic_for(cars)
+        traffic = per_frame_traffic * n if per_frame_traffic is not None else None
+        names = ["k_prep", "k_cars" if args.variant != 3 else "k_cars_t",
+                 "k_decide_t", "k_emit", "side-stream tail (k_fallback/k_slow join)"]
         pipe_ms = sum(phase_ms)
         kernels = [{"name": nm, "ms_per_step": ms, "share": ms / pipe_ms if pipe_ms else None,
                     "launches_per_step": phase_chunks if nm[0] == "k" else None}
                    for nm, ms in zip(names, phase_ms)]
         # the dominant kernel on its own: algorithmic bytes it must move per frame
-        own_bytes = {"k_prep": 204.0, "k_cars": 36.0 * args.cars, "k_decide": 160.0 + 76.0,
-                     "k_emit": 640.0 + 8.0}
+        own_bytes = {names[0]: 204.0, names[1]: 36.0 * cars, names[2]: 160.0 + 76.0,
+                     names[3]: 640.0 + 8.0}
         dom = max(kernels[:4], key=lambda k: k["ms_per_step"])
         dom_launches = max(1, phase_chunks)
         dom_ms = dom["ms_per_step"] / dom_launches
@@ -493,44 +626,46 @@ def main():
                     "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak,
                     "traffic": traffic_by_kernel.get(dom["name"])}
         line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
+            "metric": METRIC if not dense else "planned frames/sec, 64 cars per frame (BASELINE configs[4])",
+            "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.cars == N_CARS and n == FRAMES_PER_GPU else
-                       f"{n} independent synthetic frames x {args.cars} cars x 3 lanes per GPU",
-                       "frames_per_gpu": n, "cars_per_frame": args.cars,
-                       "l2_policy": f"inputs+outputs ({(204 + 36 * args.cars + 884) * n / 1e9:.1f} GB per step) are larger than the 126 MB L2",
+            "config": {"workload": workload,
+                       "frames_per_gpu": n, "frames_total": n * world, "cars_per_frame": cars,
+                       "l2_policy": f"inputs+outputs ({(204 + 36 * cars + 884) * n / 1e9:.1f} GB per step) are larger than the 126 MB L2",
                        "kernel_variant": args.variant,
-                       "step": "pp_plan_stats_batch (= pp_plan_batch + pp_stats_batch)" +
-                               (" + NCCL all-reduce(stats)" if world > 1 else "")},
+                       "step": "pp_plan_stats_batch (= pp_plan_batch + pp_stats_batch); after the "
+                               "last step pp_fstats_batch + pp_stats_reduce (the one NCCL "
+                               f"collective, {world} rank{'s' if world > 1 else ''})"},
             "e2e": {"value": e2e_value, "unit": "frames/s",
-                    "h2d_bytes_per_step": int(hf.bytes_per_frame() * n),
-                    "d2h_bytes_per_step": int(hp.bytes_per_frame() * n),
+                    "h2d_bytes_per_step": int(hf.bytes_per_frame() * e2e_n),
+                    "d2h_bytes_per_step": int(hp.bytes_per_frame() * e2e_n),
+                    "frames_per_step": e2e_n,
                     "api": "pp_plan_batch_host (pinned host buffers, chunked H2D/plan/D2H pipeline)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "pp_plan_batch pipeline (k_prep + k_cars + k_decide + k_emit, "
-                                   "4 chunks of 262,144 frames per step, planned concurrently); "
-                                   "dominant: "
-                                   + max(kernels[:4], key=lambda k: k["ms_per_step"])["name"],
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
+                         "kernel": "pp_plan_batch pipeline (k_prep + k_cars + k_decide_t + k_emit, "
+                                   "chunks of 262,144 frames, four planned concurrently); "
+                                   "dominant: " + dom["name"],
                          "kernel_ms": kern_ms, "kernels": kernels, "dominant_kernel": dominant,
                          "kernels_one_after_the_other_ms": pipe_ms, "ncu": ncu_view,
                          "algorithmic_bytes_per_frame": bytes_in + BYTES_OUT,
                          "algorithmic_bytes_per_step": alg_bytes,
                          "note": "FP64-issue / divergence bound, not HBM bound (DESIGN.md §2): "
-                                 "1,520 B against ~41 k instructions per frame, a third to a half of them FP64"},
+                                 f"{bytes_in + BYTES_OUT:,} B against tens of thousands of instructions per frame, a third to a half of them FP64"},
             "clocks": clocks,
             "stats": {"frames": int(stats[0]), "points": int(stats[1]),
-                      "lane_changes": int(stats[8])},
+                      "lane_changes": int(stats[8]),
+                      "f64": {nm: float(v) for nm, v in zip(pp.FSTAT_NAMES, fstats)},
+                      "check": stats_check},
         }
         if not args.no_cpu and world == 1:
-            fps, secs, kind, threads = time_cpu(pp, m, n, cars=args.cars)
-            line["cpu_baseline"] = {
-                "value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
-                "sample": f"all {n} frames of the workload, 1 pass, {threads} threads ({secs:.1f} s wall)"}
+            line["cpu_baseline"] = cpu_baseline_legs(pp, m, min(n, FRAMES_PER_GPU), cars)
         emit(line)
+    comm.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

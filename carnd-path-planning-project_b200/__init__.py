@@ -21,7 +21,8 @@ import numpy as np
 
 from . import abi
 from .abi import (Config, FrameBatch, Frames, PlanBatch, Plans, default_config, FLAG, FLAG_NAMES,
-                  NUM_FLAGS, STATS_LEN, PATH_LEN, PREV_KEEP, MAP_STRIDE)
+                  NUM_FLAGS, STATS_LEN, PATH_LEN, PREV_KEEP, MAP_STRIDE, FSTATS_LEN, FSTAT_NMIN,
+                  FSTAT_NAMES, COMM_ID_BYTES)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpp_b200.so")
@@ -41,9 +42,12 @@ EXPORTS = [
     "pp_set_phase_timing", "pp_get_phase_ms", "pp_speed_controller_batch",
     "pp_project_speed_batch",
     "pp_dev_alloc", "pp_dev_free", "pp_dev_upload", "pp_dev_download", "pp_dev_sync",
+    "pp_dev_set", "pp_stream_create", "pp_stream_sync", "pp_stream_destroy",
     "pp_rollouts_create", "pp_rollouts_destroy", "pp_rollouts_run", "pp_rollouts_last",
     "pp_rollouts_get_state", "pp_rollouts_stats", "pp_rollouts_set_lean", "pp_sweep_batch",
-    "pp_set_pipes", "pp_plan_stats_batch",
+    "pp_set_pipes", "pp_plan_stats_batch", "pp_synth_frames_dev", "pp_fstats_batch",
+    "pp_comm_unique_id", "pp_comm_init_rank", "pp_comm_init_all", "pp_comm_destroy",
+    "pp_comm_group_begin", "pp_comm_group_end", "pp_stats_reduce",
 ]
 
 
@@ -177,6 +181,22 @@ class DeviceFrames:
         self.n, self.max_cars = frames.n, frames.max_cars
         self.t = {k: torch.from_numpy(v).to(device) for k, v in frames.arrays().items()}
 
+    @classmethod
+    def empty(cls, n: int, max_cars: int, device="cuda") -> "DeviceFrames":
+        import torch
+        self = cls.__new__(cls)
+        self.n, self.max_cars = n, max_cars
+        tmap = {np.float64: torch.float64, np.int32: torch.int32}
+        self.t = {name: torch.empty((n,) + abi._inner(kind, max_cars), dtype=tmap[dt], device=device)
+                  for name, dt, kind in abi.FRAME_FIELDS}
+        return self
+
+    def to_host(self) -> FrameBatch:
+        fb = FrameBatch(self.n, self.max_cars)
+        for k, v in self.t.items():
+            setattr(fb, k, v.cpu().numpy())
+        return fb
+
     def struct(self) -> Frames:
         s = Frames()
         for k, v in self.t.items():
@@ -261,6 +281,72 @@ def stats_batch(plans: DevicePlans, stream=None):
     _check(lib.pp_stats_batch(C.byref(ps), C.c_int64(plans.n), C.c_void_p(out.data_ptr()),
                               C.c_void_p(stream)), "pp_stats_batch")
     return out
+
+
+def fstats_batch(plans: DevicePlans, stream=None, out=None):
+    """pp_fstats_batch -> float64[FSTATS_LEN] torch tensor on the device (minima, then maxima)."""
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    if out is None:
+        out = torch.empty(FSTATS_LEN, dtype=torch.float64, device=next(iter(plans.t.values())).device)
+    ps = plans.struct()
+    _check(lib.pp_fstats_batch(C.byref(ps), C.c_int64(plans.n), C.c_void_p(out.data_ptr()),
+                               C.c_void_p(stream)), "pp_fstats_batch")
+    return out
+
+
+def synth_frames_dev(m: Map, n: int, n_cars: int = 12, seed: int = 0x5EED, first_frame: int = 0,
+                     rare_permille: int = 20, max_cars: int | None = None,
+                     out: "DeviceFrames | None" = None, stream=None) -> "DeviceFrames":
+    """pp_synth_frames_dev: the synthetic workload generated in HBM (same bits as synth_frames)."""
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    if out is None:
+        out = DeviceFrames.empty(n, max_cars if max_cars is not None else max(n_cars, 1))
+    s = out.struct()
+    _check(lib.pp_synth_frames_dev(m.handle, C.c_uint64(seed), C.c_int64(first_frame), C.c_int64(n),
+                                   C.c_int32(n_cars), C.c_int32(rare_permille), C.byref(s),
+                                   C.c_void_p(stream)), "pp_synth_frames_dev")
+    return out
+
+
+class Comm:
+    """An ncclComm_t made through the C ABI (pp_comm_*): one process per GPU.  `exchange` ships
+    rank 0's 128-byte id to the other ranks (bytes -> bytes; e.g. a torch.distributed broadcast);
+    world == 1 needs none."""
+
+    def __init__(self, rank: int = 0, world: int = 1, exchange=None):
+        self.rank, self.world = rank, world
+        ident = (C.c_ubyte * COMM_ID_BYTES)()
+        if rank == 0:
+            _check(lib.pp_comm_unique_id(ident), "pp_comm_unique_id")
+        if world > 1:
+            raw = exchange(bytes(ident))
+            ident = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(raw)
+        self._h = C.c_void_p()
+        _check(lib.pp_comm_init_rank(ident, C.c_int(rank), C.c_int(world), C.byref(self._h)),
+               "pp_comm_init_rank")
+
+    def stats_reduce(self, stats=None, fstats=None, stream=None):
+        """pp_stats_reduce: in-place ncclSum of int64 `stats`, ncclMin / ncclMax of f64 `fstats`."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        _check(lib.pp_stats_reduce(self._h, C.c_void_p(_ptr(stats)), C.c_void_p(_ptr(fstats)),
+                                   C.c_void_p(stream)), "pp_stats_reduce")
+
+    def close(self):
+        if self._h:
+            lib.pp_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class RolloutStateHost:

@@ -36,6 +36,13 @@ STAT_FLAG0 = 9
 STAT_XSUM = STAT_FLAG0 + NUM_FLAGS
 STATS_LEN = STAT_XSUM + 1
 
+# f64 min / max statistics (pp_fstats_batch): entries [0, FSTAT_NMIN) are minima
+FSTAT_NAMES = ["min_ego_speed", "min_target_speed", "min_step_speed", "max_ego_speed",
+               "max_target_speed", "max_step_speed", "max_acc"]
+FSTAT_NMIN = 3
+FSTATS_LEN = len(FSTAT_NAMES)
+COMM_ID_BYTES = 128
+
 _dp = C.c_void_p  # every array pointer crosses the ABI as a raw address
 
 

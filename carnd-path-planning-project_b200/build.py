@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpp_b200.so")
 SOURCES = ["pp_api.cu", "pp_plan.cu", "pp_units.cu", "pp_rollout.cu", "pp_sweep.cu", "pp_map_host.cpp",
-           "pp_synth.cpp"]
+           "pp_synth.cu", "pp_comm.cu"]
 HEADERS = ["pp_device.cuh", "pp_internal.h", os.path.join("..", "..", "include", "pp.h")]
 
 NVCC_FLAGS = [
@@ -25,6 +25,7 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-O2",
     "-shared",
+    "-ldl",
 ]
 
 

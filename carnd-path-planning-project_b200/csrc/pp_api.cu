@@ -100,6 +100,18 @@ int upload_map(pp_map *m) {
     cudaGetLastError();
     return PP_E_CUDA;
   }
+  e = cudaMalloc(&m->dev_yaw, m->yaw.size() * sizeof(double));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(m->dev_yaw, m->yaw.data(), m->yaw.size() * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(m->dev_table);
+    if (m->dev_yaw) cudaFree(m->dev_yaw);
+    m->dev_table = nullptr;
+    m->dev_yaw = nullptr;
+    set_cuda_error("cudaMalloc/cudaMemcpy(yaw table)", (int)e, cudaGetErrorString(e));
+    cudaGetLastError();
+    return PP_E_CUDA;
+  }
   m->device = dev;
   return PP_OK;
 }
@@ -108,6 +120,10 @@ void free_map_device(pp_map *m) {
   if (m && m->dev_table) {
     cudaFree(m->dev_table);
     m->dev_table = nullptr;
+  }
+  if (m && m->dev_yaw) {
+    cudaFree(m->dev_yaw);
+    m->dev_yaw = nullptr;
   }
 }
 
@@ -179,6 +195,7 @@ int pp_map_create(const double *wx, const double *wy, int n, pp_map **out) {
     return rc;
   }
   m->n = n;
+  ppi::build_yaw_table(m->table, n, m->yaw);
   ppi::upload_map(m);  // failure is recorded in pp_last_cuda_error(); see above
   *out = m;
   return PP_OK;
@@ -242,6 +259,25 @@ int pp_dev_download(void *dst_host, const void *src_dev, size_t bytes) {
 }
 int pp_dev_sync(void) {
   PP_CK(cudaDeviceSynchronize(), "pp_dev_sync");
+  return PP_OK;
+}
+int pp_dev_set(int device) {
+  PP_CK(cudaSetDevice(device), "pp_dev_set");
+  return PP_OK;
+}
+int pp_stream_create(void **stream_out) {
+  if (!stream_out) return PP_E_ARG;
+  cudaStream_t st = nullptr;
+  PP_CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "pp_stream_create");
+  *stream_out = st;
+  return PP_OK;
+}
+int pp_stream_sync(void *stream) {
+  PP_CK(cudaStreamSynchronize((cudaStream_t)stream), "pp_stream_sync");
+  return PP_OK;
+}
+int pp_stream_destroy(void *stream) {
+  if (stream) PP_CK(cudaStreamDestroy((cudaStream_t)stream), "pp_stream_destroy");
   return PP_OK;
 }
 

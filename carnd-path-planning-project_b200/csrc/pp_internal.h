@@ -13,12 +13,16 @@ struct pp_map {
   std::vector<double> table;  // n * PP_MAP_STRIDE, host copy (row layout of pp.h)
   double *dev_table = nullptr;  // device copy, padded (nullptr if no CUDA device was usable)
   int device = -1;              // CUDA device the table lives on
+  std::vector<double> yaw;      // [n][3] lane-segment headings in degrees (synthetic generator)
+  double *dev_yaw = nullptr;
 };
 
 namespace ppi {
 
 // Host-side Map::Init (reference src/main.cpp:89-131): fills `table`.
 int build_map_table(const double *wx, const double *wy, int n, std::vector<double> &table);
+// atan2 of every lane segment's direction, in degrees (pp_synth.cu).
+void build_yaw_table(const std::vector<double> &table, int n, std::vector<double> &yaw);
 // CSV reader with the reference's parsing (src/main.cpp:1171-1191).
 int read_map_csv(const char *path, std::vector<double> &wx, std::vector<double> &wy);
 

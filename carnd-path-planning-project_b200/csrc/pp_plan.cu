@@ -1763,7 +1763,12 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
   if ((rc = ensure_smem(k_decide_t<true>, smem_tile)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_slow_t, smem)) != PP_OK) return rc;
   static const int decide_bulk_out = env_int("PP_DECIDE_BULK_OUT", 1, 0, 1);  // experiments
+  // persistent grids: blocks per SM each kernel may occupy (a smaller share leaves room for the
+  // kernels of the other chunks in flight; profiles/r2_grids.log)
   static const int decide_blocks = env_int("PP_DECIDE_BLOCKS", 4, 1, 16);
+  static const int prep_blocks = env_int("PP_PREP_BLOCKS", 12, 1, 16);
+  static const int cars_blocks = env_int("PP_CARS_BLOCKS", 12, 1, 16);
+  static const int emit_blocks = env_int("PP_EMIT_BLOCKS", 12, 1, 16);
   const int bulk_prev = aligned16(in->prev_x) && aligned16(in->prev_y);
 
   const bool fused = variant == 1 || (variant == 0 && n_frames < kFusedBelow);
@@ -1870,7 +1875,7 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     if (tiled) {
       // (the car arrays of a chunk start on a 16-byte boundary when those of the batch do:
       // chunks are multiples of 1024 frames)
-      k_prep<<<grid_for(cnt, 12), kBlock, smem, ls>>>(map->dev_table, map->n, *cfg, fin, sc, cnt);
+      k_prep<<<grid_for(cnt, prep_blocks), kBlock, smem, ls>>>(map->dev_table, map->n, *cfg, fin, sc, cnt);
       phase_mark(pe, 1, ls);
       if (mc > 0) {
         switch (cthreads) {
@@ -1890,7 +1895,7 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
       cudaEventRecord(side.ev_a, ls);
       cudaStreamWaitEvent(side.st, side.ev_a, 0);
       k_fallback<<<side_grid, kBlock, 0, side.st>>>(fout, sc, sc.slow_qa, sc.slow_na);
-      const int eg = grid_for(cnt, 12);
+      const int eg = grid_for(cnt, emit_blocks);
       if (paired) {
         if (sc.xsum)
           k_emit<PairOut, true><<<eg, kBlock, smem_emit, ls>>>(*cfg, fout, sc, cnt);
@@ -1919,10 +1924,10 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
       phase_mark(pe, 5, ls);
       continue;
     }
-    k_prep<<<grid_for(cnt, 12), kBlock, smem, ls>>>(map->dev_table, map->n, *cfg, fin, sc, cnt);
+    k_prep<<<grid_for(cnt, prep_blocks), kBlock, smem, ls>>>(map->dev_table, map->n, *cfg, fin, sc, cnt);
     phase_mark(pe, 1, ls);
     if (mc > 0)
-      k_cars<<<grid_for((cnt * mc + kTileK - 1) / kTileK, 12), kBlock, smem, ls>>>(
+      k_cars<<<grid_for((cnt * mc + kTileK - 1) / kTileK, cars_blocks), kBlock, smem, ls>>>(
           map->dev_table, map->n, fin, fout, sc, cnt);
     phase_mark(pe, 2, ls);
     k_decide_t<false><<<grid_for(cnt, decide_blocks), kBlock, smem_tile, ls>>>(
@@ -1933,7 +1938,7 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     cudaEventRecord(side.ev_a, ls);
     cudaStreamWaitEvent(side.st, side.ev_a, 0);
     k_fallback<<<side_grid, kBlock, 0, side.st>>>(fout, sc, sc.slow_qa, sc.slow_na);
-    const int eg = grid_for(cnt, 12);
+    const int eg = grid_for(cnt, emit_blocks);
     if (paired) {  // (a row is 400 bytes: every frame of an aligned array is aligned)
       if (sc.xsum)
         k_emit<PairOut, true><<<eg, kBlock, smem_emit, ls>>>(*cfg, fout, sc, cnt);

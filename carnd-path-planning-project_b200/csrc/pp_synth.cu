@@ -1,4 +1,4 @@
-// Synthetic telemetry frames (host).  SURVEY §8(d) config 2 / config 5.
+// Synthetic telemetry frames (host and device twins).  SURVEY §8(d) config 2 / config 5.
 //
 // The reference has no recorded telemetry, tests or fixtures, so the workload
 // the metric is quoted on ("1M independent synthetic frames, 12 cars each,
@@ -10,36 +10,55 @@
 // off-road, a car > 1000 m away, hard braking, exact ties, cold start,
 // car-following (ADJUST/KEEP), collision, crawling ego, ego exactly on a
 // waypoint.
+//
+// The generator is arithmetic only (+ - * /, integer mixing), compiled without FMA
+// contraction on both sides, so the device twin (pp_synth_frames_dev: one thread per
+// frame, BASELINE config 5 generates its 64M dense frames in HBM instead of shipping
+// 217 GB over PCIe) writes the same bits as the host loop.  The one transcendental — the
+// yaw, atan2 of a lane segment's direction — is a function of (segment, lane) only and
+// comes from a table filled on the host at map creation.
+#include <cuda_runtime.h>
+
 #include <cmath>
 #include <cstdint>
-#include <utility>
 
 #include "pp_internal.h"
 
+#define PP_HD __host__ __device__
+
 namespace {
+
+template <class T>
+PP_HD inline void swap2(T &a, T &b) {
+  const T t = a;
+  a = b;
+  b = t;
+}
 
 struct Rng {
   uint64_t key, ctr;
-  static uint64_t mix(uint64_t z) {
+  PP_HD static uint64_t mix(uint64_t z) {
     z += 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
   }
-  Rng(uint64_t seed, uint64_t frame) : key(mix(mix(seed) ^ (frame * 0xD1B54A32D192ED03ull))), ctr(0) {}
-  uint64_t next() { return mix(key + (ctr++) * 0x9E3779B97F4A7C15ull); }
-  double uni() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }  // [0,1)
-  double range(double a, double b) { return a + (b - a) * uni(); }
-  int below(int n) { return (int)(next() % (uint64_t)n); }
-  bool chance(double p) { return uni() < p; }
+  PP_HD Rng(uint64_t seed, uint64_t frame) : key(mix(mix(seed) ^ (frame * 0xD1B54A32D192ED03ull))), ctr(0) {}
+  PP_HD uint64_t next() { return mix(key + (ctr++) * 0x9E3779B97F4A7C15ull); }
+  PP_HD double uni() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }  // [0,1)
+  PP_HD double range(double a, double b) { return a + (b - a) * uni(); }
+  PP_HD int below(int n) { return (int)(next() % (uint64_t)n); }
+  PP_HD bool chance(double p) { return uni() < p; }
 };
 
 struct Track {
-  const double *t;
+  const double *t;    // n rows of PP_MAP_STRIDE doubles (un-padded)
+  const double *yaw;  // [n][3] heading in degrees of lane segment (w-1 -> w)
   int n;
-  const double *row(int i) const { return t + (size_t)(((i % n) + n) % n) * PP_MAP_STRIDE; }
+  PP_HD int wrap(int i) const { return ((i % n) + n) % n; }
+  PP_HD const double *row(int i) const { return t + (size_t)(((i % n) + n) % n) * PP_MAP_STRIDE; }
   // point on lane `lane` of segment (w-1 -> w) at ratio u, plus tangent / normal
-  void at(int w, double u, int lane, double &x, double &y, double &tx, double &ty, double &nx,
+  PP_HD void at(int w, double u, int lane, double &x, double &y, double &tx, double &ty, double &nx,
           double &ny) const {
     const double *a = row(w - 1), *b = row(w);
     const double ax = a[2 + 2 * lane], ay = a[3 + 2 * lane];
@@ -53,7 +72,7 @@ struct Track {
     ny = b[9];
   }
   // walk ds metres along lane `lane` from (w,u)
-  void walk(int &w, double &u, int lane, double ds) const {
+  PP_HD void walk(int &w, double &u, int lane, double ds) const {
     for (int guard = 0; guard < 4 * n; guard++) {
       const double len = row(w)[10 + lane];
       if (ds >= 0) {
@@ -95,7 +114,7 @@ enum Rare {
   R_COUNT
 };
 
-void synth_one(const Track &trk, uint64_t seed, int64_t frame, int n_cars, int rare_permille,
+PP_HD void synth_one(const Track &trk, uint64_t seed, int64_t frame, int n_cars, int rare_permille,
                const pp_frames *out, int64_t f) {
   Rng rng(seed, (uint64_t)frame);
   const int mc = out->max_cars;
@@ -160,7 +179,7 @@ void synth_one(const Track &trk, uint64_t seed, int64_t frame, int n_cars, int r
   if (rare == R_COLD_START) { const int opts[3] = {0, 3, 9}; prev_n[f] = opts[rng.below(3)]; }
   ego_x[f] = prev_x[0] - tx * (v / 50);
   ego_y[f] = prev_y[0] - ty * (v / 50);
-  ego_yaw[f] = std::atan2(ty, tx) * 180 / M_PI;
+  ego_yaw[f] = trk.yaw[(size_t)trk.wrap(w) * PP_NUM_LANES + lane];  // atan2(ty, tx) in degrees
   ego_mph[f] = v * 2.237;
   int tl = lane;
   if (!rng.chance(0.8)) tl = lane + (rng.chance(0.5) ? 1 : -1);
@@ -201,28 +220,79 @@ void synth_one(const Track &trk, uint64_t seed, int64_t frame, int n_cars, int r
   if (rare == R_FAR_CAR && n_cars >= 1) { cx[0] = p9x + 1500.0; cy[0] = p9y + 900.0; }
   if (rng.chance(0.05)) {  // ids need not arrive in ascending order
     for (int a = 0, b = n_cars - 1; a < b; a++, b--) {
-      std::swap(cid[a], cid[b]);
-      std::swap(cx[a], cx[b]);
-      std::swap(cy[a], cy[b]);
-      std::swap(cvx[a], cvx[b]);
-      std::swap(cvy[a], cvy[b]);
+      swap2(cid[a], cid[b]);
+      swap2(cx[a], cx[b]);
+      swap2(cy[a], cy[b]);
+      swap2(cvx[a], cvx[b]);
+      swap2(cvy[a], cvy[b]);
     }
   }
 }
 
-}  // namespace
+__global__ void __launch_bounds__(128)
+k_synth(Track trk, uint64_t seed, int64_t first_frame, int64_t n_frames, int n_cars,
+        int rare_permille, const __grid_constant__ pp_frames out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_frames; f += stride)
+    synth_one(trk, seed, first_frame + f, n_cars, rare_permille, &out, f);
+}
 
-extern "C" int pp_synth_frames(const pp_map *map, uint64_t seed, int64_t first_frame,
-                               int64_t n_frames, int32_t n_cars, int32_t rare_permille,
-                               const pp_frames *out) {
+int check_out(const pp_map *map, int64_t n_frames, int32_t n_cars, const pp_frames *out) {
   if (!map || !out || n_frames < 0) return PP_E_ARG;
   if (n_cars < 0 || n_cars > out->max_cars || out->max_cars > PP_MAX_CARS) return PP_E_RANGE;
   if (!out->ego_x || !out->ego_y || !out->ego_yaw_deg || !out->ego_speed_mph || !out->prev_n ||
       !out->prev_x || !out->prev_y || !out->target_lane_in || !out->n_cars || !out->car_id ||
       !out->car_x || !out->car_y || !out->car_vx || !out->car_vy)
     return PP_E_ARG;
-  Track trk{map->table.data(), map->n};
+  return PP_OK;
+}
+
+}  // namespace
+
+// Heading (degrees) of every lane segment, the table both generators read.
+void ppi::build_yaw_table(const std::vector<double> &table, int n, std::vector<double> &yaw) {
+  yaw.assign((size_t)n * PP_NUM_LANES, 0.0);
+  for (int w = 0; w < n; w++) {
+    const double *a = &table[(size_t)((w - 1 + n) % n) * PP_MAP_STRIDE];
+    const double *b = &table[(size_t)w * PP_MAP_STRIDE];
+    for (int lane = 0; lane < PP_NUM_LANES; lane++) {
+      const double len = b[10 + lane];
+      const double tx = (b[2 + 2 * lane] - a[2 + 2 * lane]) / len;
+      const double ty = (b[3 + 2 * lane] - a[3 + 2 * lane]) / len;
+      yaw[(size_t)w * PP_NUM_LANES + lane] = std::atan2(ty, tx) * 180 / M_PI;
+    }
+  }
+}
+
+extern "C" int pp_synth_frames(const pp_map *map, uint64_t seed, int64_t first_frame,
+                               int64_t n_frames, int32_t n_cars, int32_t rare_permille,
+                               const pp_frames *out) {
+  const int rc = check_out(map, n_frames, n_cars, out);
+  if (rc != PP_OK) return rc;
+  Track trk{map->table.data(), map->yaw.data(), map->n};
   for (int64_t f = 0; f < n_frames; f++)
     synth_one(trk, seed, first_frame + f, n_cars, rare_permille, out, f);
+  return PP_OK;
+}
+
+// The same frames written by the GPU into DEVICE buffers (asynchronous on cuda_stream).
+extern "C" int pp_synth_frames_dev(const pp_map *map, uint64_t seed, int64_t first_frame,
+                                   int64_t n_frames, int32_t n_cars, int32_t rare_permille,
+                                   const pp_frames *out_dev, void *cuda_stream) {
+  int rc = check_out(map, n_frames, n_cars, out_dev);
+  if (rc != PP_OK) return rc;
+  if ((rc = ppi::check_map_device(map, "pp_synth_frames_dev")) != PP_OK) return rc;
+  if (n_frames == 0) return PP_OK;
+  Track trk{map->dev_table + (size_t)PPD_PAD_ROWS * PP_MAP_STRIDE, map->dev_yaw, map->n};
+  const int64_t want = (n_frames + 127) / 128;
+  const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+  k_synth<<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(trk, seed, first_frame, n_frames, n_cars,
+                                                      rare_permille, *out_dev);
+  ppi::count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ppi::set_cuda_error("k_synth", (int)e, cudaGetErrorString(e));
+    return PP_E_CUDA;
+  }
   return PP_OK;
 }

@@ -199,9 +199,49 @@ int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const pp_frames 
 
 /* Aggregate statistics of a planned batch on the device:
  * stats_dev[PP_STATS_LEN] (int64, overwritten).  The multi-GPU job all-reduces
- * this vector (ncclSum) — the only collective on the path. */
+ * this vector (pp_stats_reduce, ncclSum) — the only collective on the path. */
 int pp_stats_batch(const pp_plans *plans_dev, int64_t n_frames, int64_t *stats_dev,
                    void *cuda_stream);
+
+/* f64 minimum / maximum statistics of a planned batch, computed from the plan
+ * outputs alone so that any caller can re-derive them: with V_k = (P_{k+1} - P_k) * 50 and
+ * A_k = (V_{k+1} - V_k) * 50 over a frame's n_points output points (k < n_points - 1 and
+ * k < n_points - 2), every operation in IEEE double, left to right, no fused multiply-add.
+ * Non-finite values do not take part; an entry nothing contributed to stays at +inf (minima)
+ * or -inf (maxima).  ego_speed / target_speed are optional outputs of pp_plans. */
+#define PP_FSTAT_MIN_EGO_SPEED 0     /* min over frames of ego_speed (:1273) */
+#define PP_FSTAT_MIN_TARGET_SPEED 1  /* ... of the SpeedController target (:1430,1437) */
+#define PP_FSTAT_MIN_STEP_SPEED 2    /* min over frames and k of |V_k| */
+#define PP_FSTAT_NMIN 3              /* entries [0, NMIN) reduce with min, the rest with max */
+#define PP_FSTAT_MAX_EGO_SPEED 3
+#define PP_FSTAT_MAX_TARGET_SPEED 4
+#define PP_FSTAT_MAX_STEP_SPEED 5    /* max |V_k| */
+#define PP_FSTAT_MAX_ACC 6           /* max |A_k|: peak total acceleration along the plans
+                                        (acc_T and acc_N of :930-944 combined) */
+#define PP_FSTATS_LEN 7
+/* fstats_dev[PP_FSTATS_LEN] (device, double, overwritten); asynchronous on cuda_stream. */
+int pp_fstats_batch(const pp_plans *plans_dev, int64_t n_frames, double *fstats_dev,
+                    void *cuda_stream);
+
+/* ---- the one collective of a multi-GPU job: the final reduction of the statistics ----
+ * Frames are independent, so a job shards them contiguously over the GPUs (rank r plans
+ * [r N / G, (r + 1) N / G)) and exchanges nothing until every shard is planned; then
+ * pp_stats_reduce all-reduces, in place and as one NCCL group on cuda_stream, the int64 vector
+ * (ncclSum — exact, so 1/2/4/8-GPU results are identical) and the f64 vector (ncclMin over
+ * [0, PP_FSTAT_NMIN), ncclMax over the rest); either pointer may be NULL.  nccl_comm is an
+ * ncclComm_t: the caller's own, or one made by the helpers below (one process per GPU: rank 0
+ * calls pp_comm_unique_id and ships the PP_COMM_ID_BYTES to the others by any means, every
+ * rank calls pp_comm_init_rank with its device current; one process driving several devices:
+ * pp_comm_init_all, and the per-device pp_stats_reduce calls between pp_comm_group_begin / _end).
+ * NCCL is loaded at run time (the copy already in the process if there is one). */
+#define PP_COMM_ID_BYTES 128
+int pp_comm_unique_id(void *id_out);
+int pp_comm_init_rank(const void *id, int rank, int world, void **nccl_comm_out);
+int pp_comm_init_all(int n_dev, const int *devices, void **nccl_comms_out);
+int pp_comm_destroy(void *nccl_comm);
+int pp_comm_group_begin(void);
+int pp_comm_group_end(void);
+int pp_stats_reduce(void *nccl_comm, int64_t *stats_dev, double *fstats_dev, void *cuda_stream);
 
 /* pp_plan_batch followed by pp_stats_batch in one call (stats_dev[PP_STATS_LEN], overwritten):
  * the statistics of each chunk are taken as soon as the chunk is planned, concurrently with
@@ -345,6 +385,12 @@ int pp_dev_free(void *p);
 int pp_dev_upload(void *dst_dev, const void *src_host, size_t bytes);
 int pp_dev_download(void *dst_host, const void *src_dev, size_t bytes);
 int pp_dev_sync(void);
+/* ... and what a host program driving several devices needs (tools/pp_multi.cpp): make a device
+ * current for the calling thread, a stream on the current device (cudaStreamNonBlocking). */
+int pp_dev_set(int device);
+int pp_stream_create(void **stream_out);
+int pp_stream_sync(void *stream);
+int pp_stream_destroy(void *stream);
 
 /* Device self-test of the exact-arithmetic helpers the kernels use in place of
  * generic divisions / fmod / atan2 (Markstein quotient with cached reciprocal,
@@ -361,6 +407,11 @@ int pp_selftest_math(int64_t n, uint64_t seed, int64_t *counts_dev, void *cuda_s
  * `out` holds HOST pointers (const is cast away; caller-owned). ---- */
 int pp_synth_frames(const pp_map *map, uint64_t seed, int64_t first_frame, int64_t n_frames,
                     int32_t n_cars, int32_t rare_permille, const pp_frames *out);
+/* The same frames, bit for bit, written by the GPU into DEVICE buffers (asynchronous on
+ * cuda_stream): BASELINE config 5 generates its 64M dense frames in HBM, chunk by chunk. */
+int pp_synth_frames_dev(const pp_map *map, uint64_t seed, int64_t first_frame, int64_t n_frames,
+                        int32_t n_cars, int32_t rare_permille, const pp_frames *out_dev,
+                        void *cuda_stream);
 
 /* ---- candidate sweep (BASELINE config 4) --------------------------
  * The reference plans ONE trajectory per frame and notes that "multiple

@@ -49,6 +49,8 @@ abi = load_abi()
 
 _PATHS = {
     "ref": (os.path.join(ROOT, "oracle", "_ref", "libppref.so"), "ppref_"),
+    # the same sources with the reference's own flags (no -O): a CPU-baseline figure only
+    "ref_O0": (os.path.join(ROOT, "oracle", "_ref", "libppref_O0.so"), "ppref_"),
     "oracle": (os.path.join(ROOT, "oracle", "libpporacle.so"), "ppo_"),
 }
 

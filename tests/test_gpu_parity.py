@@ -473,3 +473,65 @@ def test_plan_stats_batch_on_rare_and_poisoned_frames(pp, torch_cuda, gmap):
     got = pp.plan_stats_batch(gmap, df, b).cpu().numpy()
     assert np.array_equal(got, want), (got, want)
     assert got[0] == n and got[1] < 50 * n  # some short paths are in there
+
+
+@pytest.mark.parametrize("cars,rare", [(12, 300), (64, 100), (0, 50)])
+def test_device_generator_is_the_host_generator(pp, torch_cuda, gmap, cars, rare):
+    """pp_synth_frames_dev (one thread per frame, BASELINE config 5 generates its frames in HBM)
+    writes the same bits as the host loop, rare frames included."""
+    n, mc = 20011, max(cars, 1)
+    host = pp.synth_frames(gmap, n, cars, seed=0xD00D, first_frame=123456789, rare_permille=rare,
+                           max_cars=mc)
+    dev = pp.synth_frames_dev(gmap, n, cars, seed=0xD00D, first_frame=123456789, rare_permille=rare,
+                              max_cars=mc)
+    torch_cuda.cuda.synchronize()
+    got = dev.to_host()
+    for k, v in host.arrays().items():
+        assert np.array_equal(getattr(got, k), v, equal_nan=True), k
+
+
+def numpy_fstats(pp, plans):
+    """Mirror of pp_fstats_batch (definition in include/pp.h)."""
+    x, y, npts = plans.next_x, plans.next_y, plans.n_points
+    out = np.array([np.inf] * pp.FSTAT_NMIN + [-np.inf] * (pp.FSTATS_LEN - pp.FSTAT_NMIN))
+
+    def upd(i, vals):
+        vals = vals[np.isfinite(vals)]
+        if len(vals):
+            out[i] = min(out[i], vals.min()) if i < pp.FSTAT_NMIN else max(out[i], vals.max())
+    upd(0, plans.ego_speed), upd(3, plans.ego_speed)
+    upd(1, plans.target_speed), upd(4, plans.target_speed)
+    with np.errstate(invalid="ignore", over="ignore"):
+        vx, vy = (x[:, 1:] - x[:, :-1]) * 50, (y[:, 1:] - y[:, :-1]) * 50
+        sp = np.sqrt(vx * vx + vy * vy)
+        k = np.arange(sp.shape[1])[None, :]
+        live = sp[k < (npts[:, None] - 1)]
+        upd(2, live), upd(5, live)
+        ax, ay = (vx[:, 1:] - vx[:, :-1]) * 50, (vy[:, 1:] - vy[:, :-1]) * 50
+        acc = np.sqrt(ax * ax + ay * ay)
+        k = np.arange(acc.shape[1])[None, :]
+        upd(6, acc[k < (npts[:, None] - 2)])
+    return out
+
+
+def test_fstats_and_the_final_reduction(pp, torch_cuda, gmap):
+    """f64 min / max statistics against a numpy mirror (bitwise: sqrt and + - * only), and
+    pp_stats_reduce over a one-rank communicator made through the C ABI (the identity; the
+    N-rank case runs in bench.py --gpus N, which asserts it against a single-rank pass)."""
+    n = 50000
+    fb = pp.synth_frames(gmap, n, 12, seed=88, rare_permille=200)
+    df = pp.DeviceFrames(fb)
+    dp = pp.DevicePlans(n, 12, diag=True, cars=False)
+    st = pp.plan_stats_batch(gmap, df, dp)
+    fs = pp.fstats_batch(dp)
+    torch_cuda.cuda.synchronize()
+    want = numpy_fstats(pp, dp.to_host())
+    got = fs.cpu().numpy()
+    assert np.array_equal(got, want), (got, want)
+    assert got[pp.FSTAT_NMIN + 3] > 0 and got[0] >= 0  # some acceleration, speeds are norms
+    before_i, before_f = st.clone(), fs.clone()
+    comm = pp.Comm(0, 1)
+    comm.stats_reduce(st, fs)
+    torch_cuda.cuda.synchronize()
+    assert torch_cuda.equal(st, before_i) and torch_cuda.equal(fs, before_f)
+    comm.close()

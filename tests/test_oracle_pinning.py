@@ -200,3 +200,17 @@ def test_glue_restatement_vs_untouched_lambda(ref, oracle, pp, pmap, abi):
     assert (on == 50).all()
     assert np.nanmax(np.abs(ox - want_x) / np.abs(want_x)) < 5e-15
     assert np.nanmax(np.abs(oy - want_y) / np.abs(want_y)) < 5e-15
+
+
+def test_host_generator_reproduces_the_golden_inputs(pp, pmap):
+    """The synthetic workload is part of the measurement contract (BASELINE configs[1] / [4]):
+    the generator must keep producing, bit for bit, the frames the committed golden outputs
+    were computed from (tests/golden/make_golden.py: seeds 20261018 / 20261019, 300 permille)."""
+    import numpy as np
+    import os
+    from conftest import GOLDEN
+    for tag, n, cars, seed in (("c12", 768, 12, 20261018), ("c64", 96, 64, 20261019)):
+        z = np.load(os.path.join(GOLDEN, f"frames_{tag}.npz"))
+        fb = pp.synth_frames(pmap, n, cars, seed=seed, rare_permille=300)
+        for k, v in fb.arrays().items():
+            assert np.array_equal(v, z["in_" + k], equal_nan=True), (tag, k)
