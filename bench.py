@@ -326,6 +326,32 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa(local):
+    """Pin this rank's threads (and, by first touch, its pinned host buffers) to the CPUs of the
+    NUMA node its GPU hangs off: with one process per GPU all ranks otherwise share node 0's
+    cores and memory for their staging copies.  Returns what was done, for the record."""
+    info = {"numa_node": None, "cpus": len(os.sched_getaffinity(0)), "bound": False}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(cpus=len(cpus), bound=True)
+    except Exception as e:  # not fatal: the measurement runs unbound
+        info["error"] = str(e)[:80]
+    return info
+
+
 def make_comm(pp, dist, rank, world):
     """An ncclComm_t made through the C ABI (pp_comm_*); torch.distributed only carries rank 0's
     128-byte id to the other ranks."""
@@ -336,14 +362,13 @@ def make_comm(pp, dist, rank, world):
     return pp.Comm(rank, world, exchange if world > 1 else None)
 
 
-def single_rank_stats(pp, m, world, n, cars, first_of_rank, torch):
+def single_rank_stats(pp, m, world, n, cars, first_of_rank, torch, df, dp):
     """The statistics of all ranks' shards planned on THIS device alone (the N-rank reduced
-    vector must equal it bit for bit): shards generated in HBM one after the other."""
+    vector must equal it bit for bit): shards generated in HBM one after the other, into the
+    rank's own buffers (df / dp are overwritten; the last shard generated is rank 0's again)."""
     tot_i = torch.zeros(pp.STATS_LEN, dtype=torch.int64, device="cuda")
     tot_f = None
-    df = pp.DeviceFrames.empty(n, max(cars, 1))
-    dp = pp.DevicePlans(n, max(cars, 1), diag=True, cars=False)
-    for r in range(world):
+    for r in list(range(1, world)) + [0]:
         pp.synth_frames_dev(m, n, cars, seed=SEED, first_frame=first_of_rank(r), out=df)
         st = pp.plan_stats_batch(m, df, dp)
         fs = pp.fstats_batch(dp)
@@ -453,6 +478,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local)
+    binding = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from __graft_entry__ import load_package
@@ -564,7 +590,7 @@ def main():
     stats_check = None
     if world > 1 and not args.no_check:
         if rank == 0:
-            one_i, one_f = single_rank_stats(pp, m, world, n, cars, first_of_rank, torch)
+            one_i, one_f = single_rank_stats(pp, m, world, n, cars, first_of_rank, torch, df, dp)
             assert np.array_equal(one_i.cpu().numpy(), stats), \
                 ("N-rank int64 statistics differ from the single-rank pass", stats, one_i)
             assert np.array_equal(one_f.cpu().numpy(), fstats), \
@@ -581,7 +607,9 @@ def main():
         pinned = torch.from_numpy(v[:e2e_n]).pin_memory()
         setattr(hf, k, pinned.numpy())
         hf.__dict__.setdefault("_keep", []).append(pinned)
-    hp = pp.PlanBatch(e2e_n, mc, diag=True, cars=False)
+    # what a drop-in caller asks for: the trajectories and the per-frame integers (the eight
+    # f64 diagnostics and the followed-car ids stay optional outputs and are not requested)
+    hp = pp.PlanBatch(e2e_n, mc, diag=False, cars=False)
     for k in hp.fields:
         pinned = torch.from_numpy(getattr(hp, k)).pin_memory()
         setattr(hp, k, pinned.numpy())
@@ -598,6 +626,10 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_n / float(te[0])
+    # bytes that crossed PCIe downwards: whole rows only for chunks that are mostly cold starts
+    # (none in this workload); else 40 of the 50 columns, plus the packed first 10 of cold frames
+    n_cold = int((hf.prev_n < 10).sum())
+    e2e_d2h = (hp.bytes_per_frame() - 2 * 10 * 8) * e2e_n + n_cold * 2 * 10 * 8
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -640,9 +672,14 @@ def main():
                                f"collective, {world} rank{'s' if world > 1 else ''})"},
             "e2e": {"value": e2e_value, "unit": "frames/s",
                     "h2d_bytes_per_step": int(hf.bytes_per_frame() * e2e_n),
-                    "d2h_bytes_per_step": int(hp.bytes_per_frame() * e2e_n),
+                    "d2h_bytes_per_step": int(e2e_d2h),
                     "frames_per_step": e2e_n,
-                    "api": "pp_plan_batch_host (pinned host buffers, chunked H2D/plan/D2H pipeline)"},
+                    "host_buffer_bytes_per_frame": int(hp.bytes_per_frame()),
+                    "host_binding": binding,
+                    "api": "pp_plan_batch_host (pinned host buffers, chunked H2D/plan/D2H pipeline; "
+                           "outputs: next_x/next_y[50], n_points, lanes, ref_wp, flags; the 10 kept "
+                           "points of a frame are filled from the caller's previous points on the "
+                           "host and do not cross PCIe)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,

@@ -180,6 +180,9 @@ class DeviceFrames:
         import torch
         self.n, self.max_cars = frames.n, frames.max_cars
         self.t = {k: torch.from_numpy(v).to(device) for k, v in frames.arrays().items()}
+        if getattr(frames, "car_frozen_lane", None) is not None:  # optional held-over cars
+            for name, _ in abi.FROZEN_FIELDS:
+                self.t[name] = torch.from_numpy(getattr(frames, name)).to(device)
 
     @classmethod
     def empty(cls, n: int, max_cars: int, device="cuda") -> "DeviceFrames":

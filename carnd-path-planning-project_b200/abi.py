@@ -109,9 +109,16 @@ PLAN_DIAG = ["ego_s", "ego_d", "ego_vs", "ego_vd", "ego_speed", "ego_acc", "targ
 PLAN_CARS = ["car_s", "car_d", "car_vs", "car_vd", "car_lane", "car_next_wp"]
 
 
+# optional inputs (NULL unless set): cars held over from earlier messages (pp.h, pp_frames)
+FROZEN_FIELDS = [("car_frozen_lane", np.int32), ("car_frozen_s", np.float64),
+                 ("car_frozen_d", np.float64), ("car_frozen_vs", np.float64),
+                 ("car_frozen_vd", np.float64)]
+
+
 class Frames(C.Structure):
     _fields_ = [(n, _dp) for n, _, _ in FRAME_FIELDS] + [("max_cars", C.c_int32),
-                                                         ("reserved", C.c_int32)]
+                                                         ("reserved", C.c_int32)] + \
+               [(n, _dp) for n, _ in FROZEN_FIELDS]
 
 
 class Plans(C.Structure):
@@ -170,7 +177,19 @@ class FrameBatch:
             assert a.dtype == dt and a.flags["C_CONTIGUOUS"], name
             setattr(s, name, a.ctypes.data)
         s.max_cars = self.max_cars
+        if getattr(self, "car_frozen_lane", None) is not None:  # optional: held-over cars
+            for name, dt in FROZEN_FIELDS:
+                a = getattr(self, name)
+                assert a.dtype == dt and a.flags["C_CONTIGUOUS"] and a.shape == (self.n, self.max_cars), name
+                setattr(s, name, a.ctypes.data)
         return s
+
+    def add_frozen(self):
+        """Allocate the optional held-over-car arrays (no slot frozen)."""
+        for name, dt in FROZEN_FIELDS:
+            setattr(self, name, np.zeros((self.n, self.max_cars), dtype=dt))
+        self.car_frozen_lane[:] = -1
+        return self
 
     def slice(self, lo: int, hi: int) -> "FrameBatch":
         out = FrameBatch.__new__(FrameBatch)

@@ -60,6 +60,13 @@ inline pp_frames offset_frames(const pp_frames &a, int64_t lo) {
   if (r.car_y) r.car_y += lo * mc;
   if (r.car_vx) r.car_vx += lo * mc;
   if (r.car_vy) r.car_vy += lo * mc;
+  if (r.car_frozen_lane) {
+    r.car_frozen_lane += lo * mc;
+    r.car_frozen_s += lo * mc;
+    r.car_frozen_d += lo * mc;
+    r.car_frozen_vs += lo * mc;
+    r.car_frozen_vd += lo * mc;
+  }
   return r;
 }
 template <class T>

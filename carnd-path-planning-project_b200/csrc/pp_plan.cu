@@ -182,6 +182,27 @@ PPD_INLINE CarRes stage_car(const MapView &m, const RefState &rs, double x, doub
   return r;
 }
 
+// A slot of the car arrays: an ordinary car of the current message is matched (stage_car); a
+// car the reference still holds from an earlier message (pp_frames::car_frozen_*) keeps the
+// Frenet values of its last sighting (src/main.cpp:1194: nothing recomputes them).
+PPD_INLINE CarRes car_slot(const MapView &m, const RefState &rs, const pp_frames &in, int64_t t,
+                           double x, double y, double vx, double vy) {
+  if (in.car_frozen_lane) {
+    const int fl = in.car_frozen_lane[t];
+    if (fl >= 0) {
+      CarRes r;
+      r.lane = fl;
+      r.wp = 0;
+      r.s = in.car_frozen_s[t];
+      r.d = in.car_frozen_d[t];
+      r.vs = in.car_frozen_vs[t];
+      r.vd = in.car_frozen_vd[t];
+      return r;
+    }
+  }
+  return stage_car(m, rs, x, y, vx, vy);
+}
+
 // ---------------------------------------------------------------------------
 // Stage D+E: streaming reductions over the cars of a frame
 // (:377-445 LaneChangePlanner loop, :1388-1410 followed cars).
@@ -379,12 +400,90 @@ PPD_INLINE void plan_one_frame(const MapView &m, const pp_config &cfg, const pp_
   behav_init(b, cfg);
   const int64_t cb = f * mc;
   for (int j = 0; j < nc; j++) {
-    const CarRes r = stage_car(m, c.rs, in.car_x[cb + j], in.car_y[cb + j], in.car_vx[cb + j],
-                               in.car_vy[cb + j]);
+    const CarRes r = car_slot(m, c.rs, in, cb + j, in.car_x[cb + j], in.car_y[cb + j],
+                              in.car_vx[cb + j], in.car_vy[cb + j]);
     store_car(out, cb + j, r);
     behav_add(b, cfg, c, tl_in, in.car_id[cb + j], j, r, flags);
   }
   stage_finish(m, cfg, in, out, f, c, b, tl_in, flags);
+}
+
+// ===========================================================================
+// Variant 4: one WARP per frame — the low-latency form for small batches (a single
+// simulator's 50 Hz frames, a few hundred sessions in lockstep).  A frame's serial work cannot
+// be cut (the emission loop is one recurrence, :908-1040), but everything that is a loop over
+// independent items is spread over the 32 lanes: the closest-waypoint scan (:147-156) as six
+// candidates per lane and a __shfl_xor argmin on (distance^2, index) — lowest index wins ties,
+// like the reference's strict < in ascending order; the sensor-fusion loop (:1325-1350) with
+// one lane per car; the reductions of LaneChangePlanner and the followed-car selection
+// (:377-445, :1388-1410) as per-lane partial results merged by a shuffle butterfly.  The
+// remaining serial phases run on all lanes redundantly (identical values, identical
+// addresses): no divergence, no hand-over through memory, and a warp instruction costs the
+// same for one active lane as for 32.
+// ===========================================================================
+PPD_INLINE int warp_closest_waypoint(const MapView &m, double x, double y) {
+  const int lane = threadIdx.x & 31;
+  int closest = lane < m.n ? lane : 0;
+  double best = (m.t[closest * PP_MAP_STRIDE] - x) * (m.t[closest * PP_MAP_STRIDE] - x) +
+                (m.t[closest * PP_MAP_STRIDE + 1] - y) * (m.t[closest * PP_MAP_STRIDE + 1] - y);
+  for (int i = lane + 32; i < m.n; i += 32) {
+    const double rx = m.t[i * PP_MAP_STRIDE], ry = m.t[i * PP_MAP_STRIDE + 1];
+    const double d = (rx - x) * (rx - x) + (ry - y) * (ry - y);
+    if (d < best) {
+      closest = i;
+      best = d;
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, closest, o);
+    if (od < best || (od == best && oi < closest)) {
+      best = od;
+      closest = oi;
+    }
+  }
+  // (every distance NaN: each lane kept its own first index; the reference answers 0)
+  return __shfl_sync(0xffffffffu, closest, 0);
+}
+
+PPD_INLINE void plan_one_frame_warp(const MapView &m, const pp_config &cfg, const pp_frames &in,
+                                    const pp_plans &out, int64_t f) {
+  const int lane = threadIdx.x & 31;
+  FrameCtx c;
+  double svx, svy;
+  ego_state(in, f, c, svx, svy);
+  finish_reference(m, c.x, c.y, warp_closest_waypoint(m, c.x, c.y), c.rs);  // :1299
+  ego_match(m, cfg, c, svx, svy);
+  uint32_t flags = c.flags;
+  const int mc = in.max_cars;
+  int nc = in.n_cars[f];
+  if (nc > mc) nc = mc;
+  const int tl_in = in.target_lane_in[f];
+  Behav b;
+  behav_init(b, cfg);
+  const int64_t cb = f * mc;
+  for (int j = lane; j < nc; j += 32) {  // lane = car
+    const CarRes r = car_slot(m, c.rs, in, cb + j, in.car_x[cb + j], in.car_y[cb + j],
+                              in.car_vx[cb + j], in.car_vy[cb + j]);
+    store_car(out, cb + j, r);
+    behav_add(b, cfg, c, tl_in, in.car_id[cb + j], j, r, flags);
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int o = 1; o < 32; o <<= 1) behav_merge_xor(b, flags, o);
+  stage_finish(m, cfg, in, out, f, c, b, tl_in, flags);
+}
+
+__global__ void __launch_bounds__(kBlock)
+plan_warp(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
+          const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
+          int64_t n_frames) {
+  extern __shared__ __align__(16) double s_map[];
+  const MapView m = stage_map(s_map, map_table, n_wp);
+  const int64_t warps = (int64_t)gridDim.x * (kBlock / 32);
+  for (int64_t f = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); f < n_frames; f += warps)
+    plan_one_frame_warp(m, cfg, in, out, f);
 }
 
 // ===========================================================================
@@ -640,7 +739,7 @@ k_cars(const double *__restrict__ map_table, int n_wp, const __grid_constant__ p
       rs.ratio[0] = sc.ratio[f];
       rs.ratio[1] = sc.ratio[sc.n + f];
       rs.ratio[2] = sc.ratio[2 * sc.n + f];
-      const CarRes r = stage_car(m, rs, in.car_x[t], in.car_y[t], in.car_vx[t], in.car_vy[t]);
+      const CarRes r = car_slot(m, rs, in, t, in.car_x[t], in.car_y[t], in.car_vx[t], in.car_vy[t]);
       const int64_t slot = (int64_t)j * sc.n + f;  // car-major: k_decide reads it coalesced
       sc.car_s[slot] = r.s;
       sc.car_d[slot] = r.d;
@@ -1084,7 +1183,7 @@ k_cars_t(const double *__restrict__ map_table, int n_wp, const __grid_constant__
       rs.ratio[0] = fr0[fl];
       rs.ratio[1] = fr1[fl];
       rs.ratio[2] = fr2[fl];
-      const CarRes r = stage_car(m, rs, car0[i], car1[i], car2[i], car3[i]);
+      const CarRes r = car_slot(m, rs, in, cb0 + i, car0[i], car1[i], car2[i], car3[i]);
       store_car(out, cb0 + i, r);
       // its share of the frame's reductions, evaluated here where every lane has a car
       const double dt0 = fnp[fl] ? PP_PREV_KEEP / 50.0 : 0.0;
@@ -1663,7 +1762,7 @@ int ensure_smem(K kernel, size_t smem) {
 }  // namespace
 
 extern "C" int pp_set_kernel_variant(int variant) {
-  if (variant < 0 || variant > 3) return PP_E_ARG;
+  if (variant < 0 || variant > 4) return PP_E_ARG;
   g_variant = variant;
   return PP_OK;
 }
@@ -1692,7 +1791,8 @@ static int pipe_count() {
 // (a caller that brings its own scratch drives its own concurrency: one chunk in flight)
 size_t ppi::plan_scratch_bytes(int64_t n_frames, int max_cars) {
   const int variant = g_variant.load(std::memory_order_relaxed);
-  if (n_frames <= 0 || variant == 1 || (variant == 0 && n_frames < kFusedBelow)) return 0;
+  if (n_frames <= 0 || variant == 1 || variant == 4 || (variant == 0 && n_frames < kFusedBelow))
+    return 0;
   const int64_t chunk = chunk_for(n_frames, 1);
   const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
   const int n_buf = 1;
@@ -1745,6 +1845,7 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
   if (smem > 200 * 1024) return PP_E_RANGE;
   int rc;
   if ((rc = ensure_smem(plan_fused, smem)) != PP_OK) return rc;
+  if ((rc = ensure_smem(plan_warp, smem)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_prep, smem)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_cars, smem)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_slow, smem)) != PP_OK) return rc;
@@ -1771,10 +1872,17 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
   static const int emit_blocks = env_int("PP_EMIT_BLOCKS", 12, 1, 16);
   const int bulk_prev = aligned16(in->prev_x) && aligned16(in->prev_y);
 
-  const bool fused = variant == 1 || (variant == 0 && n_frames < kFusedBelow);
+  const bool fused = variant == 1 || variant == 4 || (variant == 0 && n_frames < kFusedBelow);
   if (fused) {
-    plan_fused<<<grid_for(n_frames, 8), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, *in, *out,
-                                                            n_frames);
+    if (variant == 1) {
+      plan_fused<<<grid_for(n_frames, 8), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, *in, *out,
+                                                              n_frames);
+    } else {  // small batches: one warp per frame
+      const int64_t want = (n_frames + kBlock / 32 - 1) / (kBlock / 32);
+      const int64_t cap = (int64_t)sm_count() * 4;
+      plan_warp<<<(int)(want < cap ? want : cap), kBlock, smem, st>>>(map->dev_table, map->n, *cfg, *in,
+                                                                     *out, n_frames);
+    }
     ppi::count_launch();
     if (stats_dev) {
       stats_kernel<<<stats_grid(n_frames), 256, 0, st>>>(*out, n_frames,

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PP_VERSION 100
+#define PP_VERSION 101
 
 /* Fixed sizes of the reference's planning step. */
 #define PP_NUM_LANES 3    /* src/main.cpp:22  NUM_LANES */
@@ -106,9 +106,10 @@ typedef struct pp_config {
  * prev_x[f*PP_PREV_KEEP + i], car_x[f*max_cars + j].
  * Fields mirror the telemetry the reference reads (src/main.cpp:1233-1252,
  * 1297,1328-1334); the unused wire fields (s, d, end_path_s/d, car s/d) are
- * not carried.  Car ids within one frame must be distinct; cars may appear in
- * any order (the reference iterates a std::map<int,Car>, i.e. ascending id,
- * and only tie-breaks depend on that order — reproduced here by id). */
+ * not carried.  Car ids within one frame must be distinct (the reference's map keeps the
+ * LAST row of a repeated id; pp::wire::parse_telemetry applies that rule); cars may appear
+ * in any order (the reference iterates a std::map<int,Car>, i.e. ascending id, and only
+ * tie-breaks depend on that order — reproduced here by id). */
 typedef struct pp_frames {
   const double *ego_x;         /* [N] telemetry x  (used when prev_n < 10, :1233) */
   const double *ego_y;         /* [N] */
@@ -126,6 +127,19 @@ typedef struct pp_frames {
   const double *car_vy;
   int32_t max_cars;            /* row length of the car arrays, <= PP_MAX_CARS */
   int32_t reserved;
+  /* Optional, all five NULL or all five set: cars the reference still holds in its persistent
+   * std::map<int,Car> although the current message does not list them (src/main.cpp:1194,
+   * 1325-1334 only touch the cars of the message).  Such a car takes part in the planning with
+   * the Frenet values of its last sighting, which the reference never recomputes:
+   * car_frozen_lane[f*max_cars + j] >= 0 marks slot j as frozen (lane = that value, s / d / vs /
+   * vd from the arrays below; its car_x / car_y are not matched, car_vx / car_vy still give its
+   * Cartesian speed to LimitSpeed, :1080); -1 = an ordinary car of the current message.
+   * include/pp_wire.hpp (pp::wire::Session) maintains this state for replayed sessions. */
+  const int32_t *car_frozen_lane; /* [N][max_cars] */
+  const double *car_frozen_s;     /* [N][max_cars] */
+  const double *car_frozen_d;
+  const double *car_frozen_vs;
+  const double *car_frozen_vd;
 } pp_frames;
 
 /* Output plans, struct of arrays.  next_x/next_y entries at and beyond
@@ -250,9 +264,12 @@ int pp_plan_stats_batch(const pp_map *map, const pp_config *cfg, const pp_frames
                         const pp_plans *out, int64_t n_frames, int64_t *stats_dev,
                         void *cuda_stream);
 
-/* Kernel selection for pp_plan_batch: 0 = auto (tiled pipeline; the fused kernel for
- * batches under 4096 frames), 1 = fused single kernel, 2 = strided pipeline (round 1),
- * 3 = tiled pipeline (frame tiles through shared memory by TMA bulk copies). */
+/* Kernel selection for pp_plan_batch: 0 = auto (the pipeline; below 4096 frames the
+ * warp-per-frame kernel), 1 = one thread per frame in a single kernel, 2 = the pipeline
+ * (k_prep, k_cars, k_decide_t, k_emit), 3 = the pipeline with the tiled cars kernel (a warp's
+ * frames' cars by TMA into shared memory, reductions in the same kernel), 4 = one warp per
+ * frame (lowest latency: closest-waypoint argmin and the per-car work spread over the lanes).
+ * All variants produce the same bits. */
 int pp_set_kernel_variant(int variant);
 /* Chunks of a large batch that pp_plan_batch keeps in flight at once on internal streams:
  * 1..8, 0 = default (4).  1 runs the kernels of the pipeline strictly one after the other,

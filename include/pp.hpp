@@ -176,6 +176,9 @@ struct Car {  // src/main.cpp:51-71
   double acc_x = 0, acc_y = 0;
   double vs = 0, vd = 0;
   int lane = 0;
+  // not in the reference: this entry was NOT in the current message; the reference still holds
+  // it in its persistent map with the s, d, vs, vd, lane of its last sighting (:1194,1325-1334)
+  bool frozen = false;
   double predicted_s(double delta_t) const { return s + vs * delta_t; }
   double predicted_d(double delta_t) const { return d + vd * delta_t; }
 };
@@ -489,6 +492,9 @@ struct Plan {
   double ego_s = 0, ego_d = 0, ego_vs = 0, ego_vd = 0, ego_speed = 0, ego_acc = 0;
   double target_speed = 0, target_time = 0;
   int next_car_id = -1, next_car_in_target_lane = -1;
+  // the frame's sensor_fusion entries after the matching loop (:1325-1350): s, d, vs, vd, lane
+  // filled in; lane == -1: lane matching failed, the reference erases the car (:1339)
+  std::vector<Car> cars;
 };
 
 class Planner {
@@ -506,6 +512,12 @@ class Planner {
     std::vector<double> ex(n), ey(n), eyaw(n), esp(n), px(n * PP_PREV_KEEP), py(n * PP_PREV_KEEP),
         cx(n * mc), cy(n * mc), cvx(n * mc), cvy(n * mc);
     std::vector<int32_t> pn(n), tl(n), nc(n), cid(n * mc);
+    bool any_frozen = false;
+    for (const Frame &f : frames)
+      for (const Car &c : f.sensor_fusion) any_frozen = any_frozen || c.frozen;
+    std::vector<int32_t> fz_lane(any_frozen ? n * mc : 0, -1);
+    std::vector<double> fz_s(fz_lane.size()), fz_d(fz_lane.size()), fz_vs(fz_lane.size()),
+        fz_vd(fz_lane.size());
     for (size_t i = 0; i < n; i++) {
       const Frame &f = frames[i];
       ex[i] = f.car_x;
@@ -526,10 +538,24 @@ class Planner {
         cy[i * mc + j] = c.y;
         cvx[i * mc + j] = c.vx;
         cvy[i * mc + j] = c.vy;
+        if (c.frozen) {
+          fz_lane[i * mc + j] = c.lane;
+          fz_s[i * mc + j] = c.s;
+          fz_d[i * mc + j] = c.d;
+          fz_vs[i * mc + j] = c.vs;
+          fz_vd[i * mc + j] = c.vd;
+        }
       }
     }
     pp_frames in;
     std::memset(&in, 0, sizeof in);
+    if (any_frozen) {
+      in.car_frozen_lane = fz_lane.data();
+      in.car_frozen_s = fz_s.data();
+      in.car_frozen_d = fz_d.data();
+      in.car_frozen_vs = fz_vs.data();
+      in.car_frozen_vd = fz_vd.data();
+    }
     in.ego_x = ex.data();
     in.ego_y = ey.data();
     in.ego_yaw_deg = eyaw.data();
@@ -568,6 +594,13 @@ class Planner {
     out.target_time = d[7].data();
     out.next_car_id = id0.data();
     out.next_car_in_target_lane = id1.data();
+    std::vector<double> cs(n * mc), cd(n * mc), cvs(n * mc), cvd(n * mc);
+    std::vector<int32_t> cl(n * mc);
+    out.car_s = cs.data();
+    out.car_d = cd.data();
+    out.car_vs = cvs.data();
+    out.car_vd = cvd.data();
+    out.car_lane = cl.data();
     check(pp_plan_batch_host(map_.handle(), &cfg_, &in, &out, (int64_t)n), "pp_plan_batch_host");
     std::vector<Plan> plans(n);
     for (size_t i = 0; i < n; i++) {
@@ -588,6 +621,15 @@ class Planner {
       p.target_time = d[7][i];
       p.next_car_id = id0[i];
       p.next_car_in_target_lane = id1[i];
+      p.cars = frames[i].sensor_fusion;
+      for (size_t j = 0; j < p.cars.size(); j++) {
+        Car &c = p.cars[j];
+        c.s = cs[i * mc + j];
+        c.d = cd[i * mc + j];
+        c.vs = cvs[i * mc + j];
+        c.vd = cvd[i * mc + j];
+        c.lane = cl[i * mc + j];
+      }
     }
     return plans;
   }

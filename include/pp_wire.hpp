@@ -14,8 +14,11 @@
 #ifndef PP_B200_WIRE_HPP
 #define PP_B200_WIRE_HPP
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -51,7 +54,8 @@ struct Value {  // a JSON value of the telemetry schema
 struct Reader {
   const char *p, *end;
   bool ok;
-  Reader(const char *b, const char *e) : p(b), end(e), ok(true) {}
+  int depth;  // nesting of the value being read; the schema needs 4 (untrusted socket input)
+  Reader(const char *b, const char *e) : p(b), end(e), ok(true), depth(0) {}
   void ws() {
     while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) p++;
   }
@@ -80,27 +84,37 @@ struct Reader {
   Value value() {
     Value v;
     ws();
-    if (p >= end) {
+    if (p >= end || depth > 16) {
       ok = false;
       return v;
     }
     if (*p == '{') {
       p++;
+      depth++;
       v.kind = Value::Object;
-      if (eat('}')) return v;
+      if (eat('}')) {
+        depth--;
+        return v;
+      }
       do {
         std::string k = string();
         if (!eat(':')) ok = false;
         v.members.emplace_back(k, value());
       } while (ok && eat(','));
       if (!eat('}')) ok = false;
+      depth--;
     } else if (*p == '[') {
       p++;
+      depth++;
       v.kind = Value::Array;
-      if (eat(']')) return v;
+      if (eat(']')) {
+        depth--;
+        return v;
+      }
       do v.items.push_back(value());
       while (ok && eat(','));
       if (!eat(']')) ok = false;
+      depth--;
     } else if (*p == '"') {
       v.kind = Value::String;
       v.str = string();
@@ -133,6 +147,10 @@ inline bool numbers(const Value *v, std::vector<double> &out) {
   return true;
 }
 inline void put_number(std::string &s, double v) {
+  if (!std::isfinite(v)) {  // nlohmann::json 3.0.0 prints a non-finite number as null
+    s += "null";            // (src/json.hpp dump_float); "nan" / "inf" are not JSON
+    return;
+  }
   char buf[40];
   std::snprintf(buf, sizeof buf, "%.15g", v);
   s += buf;
@@ -160,6 +178,9 @@ inline MessageKind parse_telemetry(const std::string &msg, int target_lane, Fram
   const detail::Value &d = j.items[1];
   const detail::Value *x = d.find("x"), *y = d.find("y"), *yaw = d.find("yaw"), *sp = d.find("speed");
   if (!x || !y || !yaw || !sp) return Malformed;
+  const detail::Value *scalars[4] = {x, y, yaw, sp};
+  for (const detail::Value *v : scalars)
+    if (v->kind != detail::Value::Number) return Malformed;  // (a non-number would read as 0)
   f = Frame();
   f.car_x = x->num;
   f.car_y = y->num;
@@ -174,6 +195,8 @@ inline MessageKind parse_telemetry(const std::string &msg, int target_lane, Fram
   if (!sf || sf->kind != detail::Value::Array) return Malformed;
   for (const detail::Value &row : sf->items) {  // [id, x, y, vx, vy, s, d] (:1328-1334)
     if (row.kind != detail::Value::Array || row.items.size() < 5) return Malformed;
+    for (int k = 0; k < 5; k++)
+      if (row.items[k].kind != detail::Value::Number) return Malformed;
     Car c;
     c.id = (int)row.items[0].num;
     c.x = row.items[1].num;
@@ -184,6 +207,60 @@ inline MessageKind parse_telemetry(const std::string &msg, int target_lane, Fram
   }
   return Telemetry;
 }
+
+// The reference's cross-frame state (src/main.cpp:1194-1195): the persistent target_lane and
+// the std::map<int,Car> sensor_fusion_cars, which OUTLIVES the frame.  Each message overwrites
+// (or creates) the entries of the cars it lists — a repeated id keeps its last row — and a car
+// that fails lane matching is erased (:1325-1340); an entry the message does not mention stays
+// where it is, with the x, y, vx, vy AND the s, d, vs, vd, lane of its last sighting, and keeps
+// taking part in LaneChangePlanner and the followed-car selection.  One Session per simulator
+// connection reproduces that: frame_from() turns a message into the frame to plan (held-over
+// cars marked frozen), update() folds the plan back into the state.
+class Session {
+ public:
+  int target_lane = 1;        // :1195
+  std::map<int, Car> cars;    // :1194
+
+  MessageKind frame_from(const std::string &msg, Frame &f) {
+    const MessageKind k = parse_telemetry(msg, target_lane, f);
+    if (k != Telemetry) return k;
+    std::set<int> listed;
+    for (const Car &row : f.sensor_fusion) {  // :1325-1334, in message order
+      Car &c = cars[row.id];
+      c.id = row.id;
+      c.x = row.x;
+      c.y = row.y;
+      c.vx = row.vx;
+      c.vy = row.vy;
+      listed.insert(row.id);
+    }
+    f.sensor_fusion.clear();
+    for (const auto &kv : cars) {  // ascending id, like the reference's iteration
+      Car c = kv.second;
+      c.frozen = listed.count(kv.first) == 0;
+      f.sensor_fusion.push_back(c);
+    }
+    return Telemetry;
+  }
+
+  void update(const Frame &f, const Plan &p) {
+    target_lane = p.target_lane;  // :1355-1369
+    for (size_t j = 0; j < f.sensor_fusion.size() && j < p.cars.size(); j++) {
+      if (f.sensor_fusion[j].frozen) continue;
+      const Car &r = p.cars[j];
+      if (r.lane < 0) {  // :1336-1340
+        cars.erase(r.id);
+        continue;
+      }
+      Car &c = cars[r.id];
+      c.s = r.s;
+      c.d = r.d;
+      c.vs = r.vs;
+      c.vd = r.vd;
+      c.lane = r.lane;
+    }
+  }
+};
 
 inline std::string control_message(const Plan &p) {  // :1461-1464
   std::string s = "42[\"control\",{\"next_x\":[";

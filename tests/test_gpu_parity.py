@@ -131,6 +131,32 @@ def test_pipeline_tile_geometries(pp, torch_cuda, gmap, oracle, cars, n):
     assert_plans_equal(got, plans_dict(want), ALL_FLAGS, bitwise_traj=False)
 
 
+@pytest.mark.parametrize("cars,n", [(0, 70), (1, 333), (12, 2500), (40, 300), (64, 257)])
+def test_warp_per_frame_kernel_is_bitwise_the_fused_kernel(pp, torch_cuda, gmap, cars, n):
+    """Variant 4 (one warp per frame: the scan, the cars and the reductions spread over the
+    lanes; the default below 4096 frames) against variant 1 (one thread per frame): every bit,
+    with ragged car counts, more cars than lanes, and rare frames."""
+    rng = np.random.default_rng(cars + 7)
+    fb = pp.synth_frames(gmap, n, cars, seed=400 + cars, rare_permille=200, max_cars=max(cars, 1))
+    if cars > 1:
+        fb.n_cars[::2] = rng.integers(0, cars + 1, len(fb.n_cars[::2]))
+    try:
+        pp.set_kernel_variant(1)
+        a = gpu_plan(pp, torch_cuda, gmap, fb)
+        pp.set_kernel_variant(4)
+        b = gpu_plan(pp, torch_cuda, gmap, fb)
+    finally:
+        pp.set_kernel_variant(0)
+    auto = gpu_plan(pp, torch_cuda, gmap, fb)
+    live = np.arange(fb.max_cars)[None, :] < np.minimum(fb.n_cars, fb.max_cars)[:, None]
+    for k in a.fields:
+        x, y, z = getattr(a, k), getattr(b, k), getattr(auto, k)
+        if k.startswith("car_"):
+            x, y, z = x[live], y[live], z[live]
+        assert np.array_equal(x, y, equal_nan=True), k
+        assert np.array_equal(x, z, equal_nan=True), ("auto", k)
+
+
 def test_unaligned_buffers_take_the_plain_copies(pp, torch_cuda, gmap):
     """Frame and plan arrays that start 8 bytes off a 16-byte boundary cannot be moved by TMA
     bulk copies: the kernels fall back to ordinary loads / stores, with identical results."""
@@ -196,12 +222,25 @@ def test_ragged_and_edge_inputs(pp, torch_cuda, gmap, oracle):
     assert int(dp.t["n_points"][0]) == 0
 
 
-def test_host_entry_point_equals_device_entry_point(pp, torch_cuda, gmap):
-    """pp_plan_batch_host (copies + chunk pipeline inside) == pp_plan_batch."""
+@pytest.mark.parametrize("cold", ["few", "some", "most"])
+def test_host_entry_point_equals_device_entry_point(pp, torch_cuda, gmap, cold):
+    """pp_plan_batch_host (copies + chunk pipeline inside) == pp_plan_batch.  The host entry
+    point brings down only the 40 new columns of a trajectory and fills the 10 kept ones from
+    the caller's previous points; cold-start frames (every column new) come down packed, chunks
+    that are mostly cold as whole rows: all three routes."""
     n = 150000  # > 2 chunks of 65536, ragged tail
     fb = pp.synth_frames(gmap, n, 12, seed=41)
+    rng = np.random.default_rng(41)
+    if cold == "some":
+        fb.prev_n[rng.random(n) < 0.1] = 3
+    elif cold == "most":
+        fb.prev_n[rng.random(n) < 0.6] = 0
+        fb.prev_n[:40000] = 47  # ... but not in the first chunk
     dev = gpu_plan(pp, torch_cuda, gmap, fb, cars=True)
     host = pp.plan_batch_host(gmap, fb)
+    host.next_x[:] = -7.0  # stale contents must not survive a second call either
+    host.next_y[:] = -7.0
+    host = pp.plan_batch_host(gmap, fb, plans=host)
     for k in host.fields:
         assert np.array_equal(getattr(host, k), getattr(dev, k), equal_nan=True), k
 

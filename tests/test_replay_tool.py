@@ -82,7 +82,7 @@ def test_replay_matches_the_untouched_reference_lambda(replay_exe, pp, ref, tmp_
     for f, r in enumerate(replies):
         assert r.startswith('42["control",')
         body = json.loads(r[2:])[1]
-        gx, gy = np.array(body["next_x"]), np.array(body["next_y"])
+        gx, gy = np.array(body["next_x"], dtype=float), np.array(body["next_y"], dtype=float)
         assert len(gx) == len(gy) == want_n[f], f
         assert np.allclose(gx, want_x[f, :want_n[f]], rtol=1e-9, atol=1e-6, equal_nan=True), f
         assert np.allclose(gy, want_y[f, :want_n[f]], rtol=1e-9, atol=1e-6, equal_nan=True), f
@@ -93,3 +93,49 @@ def test_replay_matches_the_untouched_reference_lambda(replay_exe, pp, ref, tmp_
     lane2 = json.loads(head[3].split("=", 1)[1])
     assert np.allclose(np.array(lane2), tbl[:, 6:8], atol=5.1e-5)
     assert sum(1 for ln in head if ln.startswith("result=[")) == n
+
+
+@pytest.mark.gpu
+def test_replay_keeps_the_reference_persistent_car_map(replay_exe, pp, ref, abi, tmp_path):
+    """The reference's sensor_fusion_cars map outlives the frame (src/main.cpp:1194,1325-1340):
+    a car missing from a message keeps planning with the values of its last sighting, a repeated
+    id keeps its last row, a car that fails lane matching is erased.  A session in which ids
+    drop out, come back and repeat must match the untouched lambda, which carries that map."""
+    n = 160
+    src = pp.synth_frames(pp.Map(), n, 12, seed=1234, rare_permille=120)
+    rng = np.random.default_rng(12)
+    fb = abi.FrameBatch(n, 14)
+    for k in ("ego_x", "ego_y", "ego_yaw_deg", "ego_speed_mph", "prev_n", "prev_x", "prev_y",
+              "target_lane_in"):
+        getattr(fb, k)[:] = getattr(src, k)
+    for f in range(n):
+        keep = np.flatnonzero(rng.random(12) < (1.0 if f % 7 == 0 else 0.6))  # ids drop out / return
+        rows = list(keep)
+        if f % 5 == 3 and len(rows):  # a repeated id: the second row (another car's place) wins
+            rows.append(rows[0])
+        fb.n_cars[f] = len(rows)
+        for j, r in enumerate(rows):
+            pos = r if j < len(keep) else (r + 5) % 12
+            fb.car_id[f, j] = src.car_id[f, r]
+            fb.car_x[f, j], fb.car_y[f, j] = src.car_x[f, pos], src.car_y[f, pos]
+            fb.car_vx[f, j], fb.car_vy[f, j] = src.car_vx[f, pos], src.car_vy[f, pos]
+    want_x, want_y, want_n = ref.lambda_sequence(fb)
+    session = tmp_path / "session.txt"
+    session.write_text("\n".join(telemetry_message(fb, f) for f in range(n)) + "\n")
+    res = subprocess.run([replay_exe, "--map", CSV, str(session)], capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0, res.stderr
+    replies = (tmp_path / "session.txt.out").read_text().splitlines()
+    assert len(replies) == n
+    for f, r in enumerate(replies):
+        body = json.loads(r[2:])[1]
+        gx, gy = np.array(body["next_x"], dtype=float), np.array(body["next_y"], dtype=float)
+        assert len(gx) == len(gy) == want_n[f], f
+        assert np.allclose(gx, want_x[f, :want_n[f]], rtol=1e-9, atol=1e-6, equal_nan=True), f
+        assert np.allclose(gy, want_y[f, :want_n[f]], rtol=1e-9, atol=1e-6, equal_nan=True), f
+    # ... and it does matter: without the held-over cars some plans differ
+    stateless = [pp.plan_batch_host(pp.Map(), fb.slice(f, f + 1)) for f in range(1, n)]
+    diff = sum(1 for f, p in enumerate(stateless, start=1)
+               if not np.allclose(p.next_x[0, :want_n[f]], want_x[f, :want_n[f]], rtol=1e-9,
+                                  atol=1e-6, equal_nan=True))
+    assert diff > 0

@@ -198,6 +198,9 @@ int main(int argc, char **argv) {
       }
       CHECK(pp_stream_sync(d.stream));
       plan_shard(d, cfg);  // warm-up
+      bar.wait();          // (the main thread warms the communicators up: NCCL sets its
+      bar.wait();          //  channels up at the first collective, about a second)
+      CHECK(pp_stream_sync(d.stream));
       bar.wait();          // ---- every device ready, inputs resident: the clock starts
       for (int k = 0; k < steps; k++) plan_shard(d, cfg);
       CHECK(pp_dev_upload(d.stats_dev, d.stats.data(), PP_STATS_LEN * sizeof(int64_t)));
@@ -210,16 +213,22 @@ int main(int argc, char **argv) {
       bar.wait();  // ---- the clock stops
     });
   }
+  auto reduce_all = [&]() {
+    CHECK(pp_comm_group_begin());
+    for (int g = 0; g < G; g++) {
+      CHECK(pp_dev_set(g));
+      CHECK(pp_stats_reduce(comms[g], dev[g].stats_dev, dev[g].fstats_dev, dev[g].stream));
+    }
+    CHECK(pp_comm_group_end());
+  };
+  bar.wait();
+  reduce_all();  // warm-up (values are overwritten before the timed reduction)
+  bar.wait();
   bar.wait();
   const auto t0 = std::chrono::steady_clock::now();
   bar.wait();
   const auto t_plan = std::chrono::steady_clock::now();
-  CHECK(pp_comm_group_begin());
-  for (int g = 0; g < G; g++) {
-    CHECK(pp_dev_set(g));
-    CHECK(pp_stats_reduce(comms[g], dev[g].stats_dev, dev[g].fstats_dev, dev[g].stream));
-  }
-  CHECK(pp_comm_group_end());
+  reduce_all();
   bar.wait();
   bar.wait();
   const auto t1 = std::chrono::steady_clock::now();

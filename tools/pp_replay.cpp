@@ -5,7 +5,8 @@
 // Each session file holds one websocket text message per line, as the Udacity simulator sends
 // them (42["telemetry",{...}]).  The sessions advance in lockstep: step k plans the k-th message
 // of every session in ONE pp::Planner::plan call (a batch of #sessions frames), carries each
-// session's target_lane (src/main.cpp:1195) and writes the reply the reference would send
+// session's cross-frame state (target_lane and the persistent car map, src/main.cpp:1194-1195:
+// pp::wire::Session) and writes the reply the reference would send
 // (42["control",{...}] / 42["manual",{}]) to <session>.out, one per line.
 #include <cstdio>
 #include <fstream>
@@ -51,7 +52,7 @@ int main(int argc, char **argv) {
         return 66;
       }
     }
-    std::vector<int> target_lane(ns, 1);  // :1195
+    std::vector<pp::wire::Session> session(ns);  // :1194-1195
     long frames = 0, steps = 0;
     for (;;) {
       std::vector<pp::Frame> batch;
@@ -62,7 +63,7 @@ int main(int argc, char **argv) {
         if (!std::getline(in[s], line)) continue;
         any = true;
         pp::Frame f;
-        switch (pp::wire::parse_telemetry(line, target_lane[s], f)) {
+        switch (session[s].frame_from(line, f)) {
           case pp::wire::Telemetry:
             batch.push_back(f);
             owner.push_back(s);
@@ -83,7 +84,7 @@ int main(int argc, char **argv) {
         const std::vector<pp::Plan> plans = planner.plan(batch);
         for (size_t k = 0; k < plans.size(); k++) {
           const size_t s = owner[k];
-          target_lane[s] = plans[k].target_lane;
+          session[s].update(batch[k], plans[k]);
           out[s] << pp::wire::control_message(plans[k]) << "\n";
           if (log) log->frame(batch[k], plans[k]);
         }
