@@ -40,7 +40,7 @@ EXPORTS = [
     "pp_get_frenet_batch", "pp_get_xy_batch", "pp_synth_frames", "pp_selftest_math",
     "pp_lane_change_batch", "pp_limit_speed_batch", "pp_trajectory_build_batch",
     "pp_set_phase_timing", "pp_get_phase_ms", "pp_speed_controller_batch",
-    "pp_project_speed_batch",
+    "pp_project_speed_batch", "pp_control_points_batch",
     "pp_dev_alloc", "pp_dev_free", "pp_dev_upload", "pp_dev_download", "pp_dev_sync",
     "pp_dev_set", "pp_stream_create", "pp_stream_sync", "pp_stream_destroy",
     "pp_rollouts_create", "pp_rollouts_destroy", "pp_rollouts_run", "pp_rollouts_last",

@@ -31,7 +31,7 @@ struct pp_rollouts {
   int64_t *stats_sum;  // running sum of the per-tick statistics over all ticks
   // Rollouts are independent, so they are cut into kGroups ranges that tick on their own
   // streams: one group's short kernels and side-stream tail overlap the other groups' work.
-  static constexpr int kGroups = 4;
+  static constexpr int kGroups = 8;  // streams that exist; PP_ROLLOUT_GROUPS of them are used
   cudaStream_t gs[kGroups] = {};
   cudaEvent_t g_done[kGroups] = {};
   cudaEvent_t fork = nullptr;
@@ -482,7 +482,12 @@ int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStre
   // device rows of the padded table: logical row 0 starts PPD_PAD_ROWS rows in
   const Track trk{r->map->dev_table + (size_t)PPD_PAD_ROWS * PP_MAP_STRIDE, r->map->n, PP_MAP_STRIDE};
   // groups: contiguous ranges of rollouts (at least 4096 each, so that small jobs stay whole)
-  int groups = pp_rollouts::kGroups;
+  static const int want_groups = [] {
+    const char *e = getenv("PP_ROLLOUT_GROUPS");
+    const int v = e && *e ? atoi(e) : 4;
+    return v < 1 ? 1 : (v > pp_rollouts::kGroups ? pp_rollouts::kGroups : v);
+  }();
+  int groups = want_groups;
   while (groups > 1 && r->n / groups < 4096) groups--;
   const int64_t per = (r->n + groups - 1) / groups;
   const int mc = r->fr.max_cars;

@@ -156,6 +156,29 @@ __global__ void k_limit_speed(const __grid_constant__ pp_config cfg, const doubl
   flags_o[i] = flags;
 }
 
+// TrajectoryBuilder's control points alone (:638-768), map frame, as the reference logs them.
+__global__ void k_control_points(const double *table, int n_wp, const double *pos_x,
+                                 const double *pos_y, const int32_t *target_lane,
+                                 const double *ego_d, const double *ego_vd, const double *sc_start,
+                                 double *out_x, double *out_y, int32_t *out_n, int64_t n) {
+  extern __shared__ __align__(16) double s_map[];
+  const MapView m = stage_map(s_map, table, n_wp);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  RefState rs;
+  init_reference(m, pos_x[i], pos_y[i], rs);
+  uint32_t flags = 0;
+  double cx[6], cy[6];
+  const int ncp = traj_control_points(m, rs, pos_x[i], pos_y[i], target_lane[i], ego_d[i], ego_vd[i],
+                                      sc_start[i], flags, cx, cy);
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    out_x[i * 6 + k] = k < ncp ? cx[k] : __longlong_as_double(0x7ff8000000000000ll);
+    out_y[i * 6 + k] = k < ncp ? cy[k] : __longlong_as_double(0x7ff8000000000000ll);
+  }
+  out_n[i] = ncp;
+}
+
 __global__ void k_trajectory(const double *table, int n_wp, const __grid_constant__ pp_config cfg,
                              const int32_t *prev_n, const double *prev_x, const double *prev_y,
                              const double *ego_x, const double *ego_y, const double *yaw,
@@ -444,6 +467,22 @@ int pp_trajectory_build_batch(const pp_map *map, const pp_config *cfg, const int
       map->dev_table, map->n, *cfg, prev_n, prev_x, prev_y, ego_x, ego_y, ego_yaw_deg, target_lane,
       ego_d, ego_vd, sc_start, sc_target, sc_time, out_x, out_y, out_n, out_flags, n);
   return finish("k_trajectory");
+}
+
+int pp_control_points_batch(const pp_map *map, const double *pos_x, const double *pos_y,
+                            const int32_t *target_lane, const double *ego_d, const double *ego_vd,
+                            const double *sc_start, double *out_x, double *out_y, int32_t *out_n,
+                            int64_t n, void *stream) {
+  int rc = need_map(map, "pp_control_points_batch");
+  if (rc != PP_OK) return rc;
+  if (!pos_x || !pos_y || !target_lane || !ego_d || !ego_vd || !sc_start || !out_x || !out_y ||
+      !out_n || n < 0)
+    return PP_E_ARG;
+  if (n == 0) return PP_OK;
+  k_control_points<<<grid_for(n), kB, map_smem(map), (cudaStream_t)stream>>>(
+      map->dev_table, map->n, pos_x, pos_y, target_lane, ego_d, ego_vd, sc_start, out_x, out_y,
+      out_n, n);
+  return finish("k_control_points");
 }
 
 int pp_project_speed_batch(const pp_map *map, const double *vx, const double *vy,

@@ -383,6 +383,16 @@ int pp_trajectory_build_batch(const pp_map *map, const pp_config *cfg, const int
                               double *out_y, int32_t *out_n, uint32_t *out_flags, int64_t n,
                               void *cuda_stream);
 
+/* The control points of TrajectoryBuilder::build alone (src/main.cpp:638-768), in the map
+ * frame, as the reference logs them (control_points=, :779-781): the start point (pos_x,
+ * pos_y) = the last kept previous point, or the telemetry pose on a cold start; then up to 5
+ * points on the centre line of target_lane.  sc_start = SpeedController::start_speed (the ego
+ * speed).  out_x / out_y [n][6] (quiet NaN beyond out_n[n]). */
+int pp_control_points_batch(const pp_map *map, const double *pos_x, const double *pos_y,
+                            const int32_t *target_lane, const double *ego_d, const double *ego_vd,
+                            const double *sc_start, double *out_x, double *out_y, int32_t *out_n,
+                            int64_t n, void *cuda_stream);
+
 /* SpeedController (src/main.cpp:488-548) on n explicit controllers
  * (start, target, time, shift [n], all read; target/time/shift may be rewritten):
  *   op 0  get_speed(a)                 -> out[n]            (:503-512)

@@ -453,6 +453,26 @@ class TrajectoryBuilder {  // src/main.cpp:550-1049
     for (int i = 0; i < n; i++) r[i] = Point(x[i], y[i]);
     return r;
   }
+
+  // The builder's control points alone (:638-768; a local of build() in the reference, which
+  // writes them to trajectory.log as control_points=): (pos_x, pos_y) = the last kept previous
+  // point, or the telemetry pose on a cold start; start_speed = the SpeedController's.
+  static std::vector<Point> control_points(Map &map, double pos_x, double pos_y, int target_lane,
+                                           double ego_d, double ego_vd, double start_speed) {
+    using detail::one;
+    int32_t tl = target_lane;
+    detail::Dev<int32_t> dtl(&tl, 1), on(1);
+    detail::Dev<double> px = one(pos_x), py = one(pos_y), ed = one(ego_d), evd = one(ego_vd),
+                        s0 = one(start_speed), ox(6), oy(6);
+    check(pp_control_points_batch(map.handle(), px.get(), py.get(), dtl.get(), ed.get(), evd.get(),
+                                  s0.get(), ox.get(), oy.get(), on.get(), 1, nullptr),
+          "pp_control_points_batch");
+    const int n = on.first();
+    const std::vector<double> x = ox.to_host(), y = oy.to_host();
+    std::vector<Point> r(n);
+    for (int i = 0; i < n; i++) r[i] = Point(x[i], y[i]);
+    return r;
+  }
 };
 
 namespace tk {

@@ -279,14 +279,15 @@ inline std::string control_message(const Plan &p) {  // :1461-1464
 inline std::string manual_message() { return "42[\"manual\",{}]"; }  // :1470
 
 // trajectory.log as the reference writes it when need_log is set: the map header once, then per
-// frame the kept previous points and the resulting trajectory.  (control_points= and the
-// free-text diagnostics of the reference are internal to its builder; the per-frame flags
-// line carries the same information as bits.)
+// frame, in the reference's order, "first control dist", the kept previous points, the builder's
+// control points (:772-781) and the resulting trajectory (:1044-1046) — the arrays
+// DrawLines.ipynb plots.  The free-text diagnostics of the individual branches are carried as
+// bits on the flags line.
 class TrajectoryLog {
  public:
   TrajectoryLog(const std::string &path, Map &map, const std::vector<double> &wx,
                 const std::vector<double> &wy)
-      : f_(std::fopen(path.c_str(), "wt")) {
+      : f_(std::fopen(path.c_str(), "wt")), map_(&map) {
     if (!f_) throw Error(PP_E_IO, "cannot open " + path);
     std::fprintf(f_, "wpmap=[");  // :1200-1202
     for (size_t i = 0; i < wx.size(); i++) std::fprintf(f_, "%s[%.4f,%.4f]", i == 0 ? "" : ",", wx[i], wy[i]);
@@ -308,9 +309,19 @@ class TrajectoryLog {
     std::fprintf(f_, "ego lane %d target lane %d\n", out.ego_lane, in.target_lane);  // :376
     std::fprintf(f_, "flags=0x%x target_lane=%d\n", out.flags, out.target_lane);
     const size_t keep = in.previous_path_x.size() >= PP_PREV_KEEP ? PP_PREV_KEEP : 0;  // :1261-1268
+    const double pos_x = keep ? in.previous_path_x[keep - 1] : in.car_x;  // :583-600
+    const double pos_y = keep ? in.previous_path_y[keep - 1] : in.car_y;
+    const std::vector<Point> cp = TrajectoryBuilder::control_points(
+        *map_, pos_x, pos_y, out.target_lane, out.ego_d, out.ego_vd, out.ego_speed);
+    if (cp.size() > 1)  // :772-775 (the bare "]" closes a commented-out array there)
+      std::fprintf(f_, "first control dist %.2f\n]\n", (Point(pos_x, pos_y) - cp[1]).length());
     std::fprintf(f_, "prev_trajectory=[");  // :776-778
     for (size_t i = 0; i < keep; i++)
       std::fprintf(f_, "%s[%.4f,%.4f]", i == 0 ? "" : ",", in.previous_path_x[i], in.previous_path_y[i]);
+    std::fprintf(f_, "]\n");
+    std::fprintf(f_, "control_points=[");  // :779-781
+    for (size_t i = 0; i < cp.size(); i++)
+      std::fprintf(f_, "%s[%.4f,%.4f]", i == 0 ? "" : ",", cp[i].x, cp[i].y);
     std::fprintf(f_, "]\n");
     std::fprintf(f_, "result=[");  // :1044-1046
     for (size_t i = 0; i < out.next_x.size(); i++)
@@ -321,6 +332,7 @@ class TrajectoryLog {
 
  private:
   std::FILE *f_;
+  Map *map_;
 };
 
 }  // namespace wire

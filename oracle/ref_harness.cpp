@@ -354,6 +354,26 @@ int ppref_plan_frames(ppref_map *m, const pp_frames *in, const pp_plans *out, in
   return PP_OK;
 }
 
+// The same with the reference's trajectory.log sites writing to `log_path` (single thread): the
+// text the reference's classes print for these frames (control_points=, result=, ...).
+int ppref_plan_frames_log(ppref_map *m, const pp_frames *in, const pp_plans *out, int64_t n,
+                          const char *log_path) {
+  if (!m || !in || !out || !log_path) return PP_E_ARG;
+  FILE *f = fopen(log_path, "wt");
+  if (!f) return PP_E_IO;
+  fLog = f;
+  Map local = m->map;
+  for (int64_t i = 0; i < n; i++) {
+    t_flags = 0;
+    fprintf(f, "frame %lld\n", (long long)i);
+    plan_one(local, in, out, i);
+    if (out->flags) out->flags[i] = t_flags;
+  }
+  fLog = NULL;
+  fclose(f);
+  return PP_OK;
+}
+
 // ---- unit exports --------------------------------------------------------
 
 void ppref_distancesq_pt_seg(const double *px, const double *py, const double *ax,

@@ -111,6 +111,16 @@ class Checker:
         assert rc == 0, rc
         return plans
 
+    def plan_with_log(self, frames, log_path: str):
+        """ref only: plan with the reference's trajectory.log sites writing to log_path."""
+        assert self.kind.startswith("ref")
+        plans = abi.PlanBatch(frames.n, frames.max_cars, diag=True, cars=True)
+        fs, ps = frames.struct(), plans.struct()
+        rc = self.lib.ppref_plan_frames_log(self.map, C.byref(fs), C.byref(ps), C.c_int64(frames.n),
+                                            log_path.encode())
+        assert rc == 0, rc
+        return plans
+
     def plan_into(self, frames, plans, threads: int = 1, want_flags: bool = False):
         fs, ps = frames.struct(), plans.struct()
         rc = self._fn("plan_frames")(self.map, C.byref(fs), C.byref(ps), C.c_int64(frames.n),

@@ -139,3 +139,44 @@ def test_replay_keeps_the_reference_persistent_car_map(replay_exe, pp, ref, abi,
                if not np.allclose(p.next_x[0, :want_n[f]], want_x[f, :want_n[f]], rtol=1e-9,
                                   atol=1e-6, equal_nan=True))
     assert diff > 0
+
+
+@pytest.mark.gpu
+def test_trajectory_log_control_points_match_the_reference_log(replay_exe, pp, ref, tmp_path):
+    """trajectory.log: the builder's control points (control_points=, src/main.cpp:779-781) and the
+    "first control dist" line against the text the reference's own classes write for the same
+    frames (4 decimals, as DrawLines.ipynb reads them)."""
+    import re
+    n = 90
+    fb = pp.synth_frames(pp.Map(), n, 12, seed=777, rare_permille=100)
+    session = tmp_path / "session.txt"
+    session.write_text("\n".join(telemetry_message(fb, f) for f in range(n)) + "\n")
+    log = tmp_path / "trajectory.log"
+    res = subprocess.run([replay_exe, "--map", CSV, "--log", str(log), str(session)],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr
+    ours = log.read_text().splitlines()
+    # the replay carries target_lane from plan to plan (:1195): give the class harness the same
+    tl_out = [int(m.group(1)) for ln in ours for m in [re.match(r"flags=0x[0-9a-f]+ target_lane=(\d)", ln)] if m]
+    assert len(tl_out) == n
+    fb.target_lane_in[0] = 1
+    fb.target_lane_in[1:] = tl_out[:-1]
+    ref_log = tmp_path / "ref.log"
+    ref.plan_with_log(fb, str(ref_log))
+    theirs = ref_log.read_text().splitlines()
+
+    def arrays(lines, key):
+        return [np.array(json.loads(re.sub(r"-?nan", "NaN", ln.split("=", 1)[1])), dtype=float).reshape(-1, 2)
+                for ln in lines if ln.startswith(key + "=[")]
+    a, b = arrays(ours, "control_points"), arrays(theirs, "control_points")
+    assert len(a) == len(b) == n
+    for f in range(n):
+        assert a[f].shape == b[f].shape, (f, a[f].shape, b[f].shape)
+        assert np.allclose(a[f], b[f], atol=1.01e-4, equal_nan=True), f
+    da = [float(ln.split()[-1]) for ln in ours if ln.startswith("first control dist")]
+    db = [float(ln.split()[-1]) for ln in theirs if ln.startswith("first control dist")]
+    assert len(da) == len(db) == n and np.allclose(da, db, atol=0.0101)
+    ra, rb = arrays(ours, "result"), arrays(theirs, "result")
+    assert len(ra) == len(rb) == n
+    for f in range(n):
+        assert ra[f].shape == rb[f].shape and np.allclose(ra[f], rb[f], atol=1.01e-4, equal_nan=True), f
