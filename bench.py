@@ -146,6 +146,23 @@ def run_reference(args):
     return 0
 
 
+def fp64_roofline(kernel):
+    """The compute-bound workloads' roofline: share of the FP64 pipe's cycles the dominant kernel
+    keeps busy (ncu sm__pipe_fp64_cycles_active, committed capture profiles/fp64_view.json) — the
+    FP64 (non-tensor) issue rate of the B200 measured with profiles/fp64_peak.cu is the peak."""
+    try:
+        v = json.load(open(os.path.join(ROOT, "profiles", "fp64_view.json")))
+        k = v["kernels"][kernel]
+        pct = k["fp64_pipe_active_pct"]
+        return {"bound": "fp64", "kernel": kernel, "achieved": pct * v["fp64_peak"]["tflops"] / 100.0,
+                "peak": v["fp64_peak"]["tflops"], "unit": "TFLOP/s-equivalent of FP64 pipe cycles",
+                "frac": pct / 100.0, "issue_active_pct": k["issue_active_pct"],
+                "active_lanes_per_warp_instr": k["active_lanes_per_warp_instr"],
+                "traffic": None, "source": v["source"]}
+    except Exception:
+        return None
+
+
 def run_rollouts(args):
     """BASELINE configs[2]: closed-loop rollouts, device-resident simulator + planner.
     One step = --ticks ticks of every rollout; value = ego-frames (rollout-ticks) per second."""
@@ -195,6 +212,10 @@ def run_rollouts(args):
                                        f"{args.cars} cars, consume_k={args.consume_k}",
                            "ms_per_tick": ms / steps / ticks},
                 "gpu_launches": int(pp.launch_count() - launches0), "clocks": clocks,
+                "roofline": {"bound": "launch latency", "note": "a tick is a chain of eight dependent "
+                             "short kernels per stream group (8 groups); the simulator kernels keep "
+                             "the issue slots 3-5 % busy", "sim_kernels": {
+                                 k: fp64_roofline(k) for k in ("k_sim_frames", "k_sim_advance")}},
                 "stats": {"frames": int(stats[0]), "points": int(stats[1]),
                           "lane_changes": int(stats[8])}}
         emit(line)
@@ -252,6 +273,7 @@ def run_sweep(args):
                                        f"8 times) per GPU, {args.cars} cars",
                            "frames_per_s": world * n * steps / (ms * 1e-3)},
                 "gpu_launches": int(pp.launch_count() - launches0), "clocks": clocks,
+                "roofline": fp64_roofline("k_sweep_emit"),
                 "stats": {"winning_lane_hist": [int((best // 128 == k).sum()) for k in range(3)]}}
         emit(line)
     if world > 1:
@@ -626,10 +648,7 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_n / float(te[0])
-    # bytes that crossed PCIe downwards: whole rows only for chunks that are mostly cold starts
-    # (none in this workload); else 40 of the 50 columns, plus the packed first 10 of cold frames
-    n_cold = int((hf.prev_n < 10).sum())
-    e2e_d2h = (hp.bytes_per_frame() - 2 * 10 * 8) * e2e_n + n_cold * 2 * 10 * 8
+    e2e_d2h = hp.bytes_per_frame() * e2e_n
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -677,9 +696,7 @@ def main():
                     "host_buffer_bytes_per_frame": int(hp.bytes_per_frame()),
                     "host_binding": binding,
                     "api": "pp_plan_batch_host (pinned host buffers, chunked H2D/plan/D2H pipeline; "
-                           "outputs: next_x/next_y[50], n_points, lanes, ref_wp, flags; the 10 kept "
-                           "points of a frame are filled from the caller's previous points on the "
-                           "host and do not cross PCIe)"},
+                           "outputs: next_x/next_y[50], n_points, lanes, ref_wp, flags)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,

@@ -8,7 +8,6 @@
 #include <cstring>
 #include <mutex>
 #include <string>
-#include <thread>
 
 #include "pp_internal.h"
 
@@ -342,26 +341,15 @@ struct Staging {
   cudaStream_t streams[kStreams] = {};
   char *in_buf[kStreams] = {};
   char *out_buf[kStreams] = {};
-  int32_t *cold_idx[kStreams] = {};  // device: chunk-relative indices of the cold-start frames
-  double *cold_pack[kStreams] = {};  // device: their first 10 points, [2][count][10]
-  double *cold_host = nullptr;       // pinned: the packs of a whole call, chunk after chunk
-  size_t cold_host_cap = 0;          // frames
   size_t in_bytes = 0, out_bytes = 0;
   void release() {
     for (int i = 0; i < kStreams; i++) {
       if (in_buf[i]) cudaFree(in_buf[i]);
       if (out_buf[i]) cudaFree(out_buf[i]);
-      if (cold_idx[i]) cudaFree(cold_idx[i]);
-      if (cold_pack[i]) cudaFree(cold_pack[i]);
       if (streams[i]) cudaStreamDestroy(streams[i]);
       in_buf[i] = out_buf[i] = nullptr;
-      cold_idx[i] = nullptr;
-      cold_pack[i] = nullptr;
       streams[i] = nullptr;
     }
-    if (cold_host) cudaFreeHost(cold_host);
-    cold_host = nullptr;
-    cold_host_cap = 0;
     cap = 0;
   }
   ~Staging() { release(); }
@@ -380,29 +368,6 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
       return PP_E_CUDA;                                             \
     }                                                               \
   } while (0)
-
-// Columns [0, PP_PREV_KEEP) of the rows idx[i] of a [n][PP_PATH_LEN] array pair, packed:
-// pack[(0 * count + i) * 10 + k] = x, pack[(1 * count + i) * 10 + k] = y.
-__global__ void k_gather_head(const double *__restrict__ x, const double *__restrict__ y,
-                              const int32_t *__restrict__ idx, int count, double *__restrict__ pack) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count * PP_PREV_KEEP) return;
-  const int i = t / PP_PREV_KEEP, k = t - i * PP_PREV_KEEP;
-  const int64_t f = idx[i];
-  pack[(size_t)i * PP_PREV_KEEP + k] = x[f * PP_PATH_LEN + k];
-  pack[((size_t)count + i) * PP_PREV_KEEP + k] = y[f * PP_PATH_LEN + k];
-}
-
-int host_threads() {
-  static const int v = [] {
-    const char *e = getenv("PP_HOST_FILL_THREADS");
-    if (e && *e) return atoi(e) > 0 ? atoi(e) : 1;
-    const unsigned hc = std::thread::hardware_concurrency();
-    const int t = hc >= 16 ? 6 : (hc >= 8 ? 4 : (hc >= 4 ? 2 : 1));
-    return t;
-  }();
-  return v;
-}
 
 }  // namespace
 
@@ -475,74 +440,20 @@ extern "C" int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const
     sg.out_bytes = out_bpf;
   }
 
-  // The first 10 points of a plan are the caller's own previous points, verbatim, whenever the
-  // frame had 10 of them (:578, :1261): those 160 of 800 trajectory bytes per frame need not
-  // cross PCIe again.  Only columns [10, 50) come down (a pitched copy); the kept columns are
-  // filled here on the host, by a few threads, while the copies and kernels run.  The frames
-  // WITHOUT a previous path (cold starts: every column is new) are known up front from
-  // prev_n, so their first 10 columns are gathered on the device and come down packed.
-  static const bool pitched = [] {
-    const char *e = getenv("PP_HOST_PITCHED");  // experiments: 0 = whole rows as in round 1
-    return !(e && *e == '0');
-  }();
-  std::vector<std::vector<int32_t>> cold(sizes.size());
-  std::vector<size_t> cold_off(sizes.size() + 1, 0);
-  std::vector<char> flat(sizes.size(), pitched ? 0 : 1);
-  if (pitched) {
-    int64_t lo0 = 0;
-    for (size_t ci = 0; ci < sizes.size(); lo0 += sizes[ci], ci++) {
-      for (int64_t f = 0; f < sizes[ci]; f++)
-        if (in->prev_n[lo0 + f] < PP_PREV_KEEP) cold[ci].push_back((int32_t)f);
-      if ((int64_t)cold[ci].size() * 4 > sizes[ci]) {  // mostly cold: whole rows, as before
-        flat[ci] = 1;
-        cold[ci].clear();
-      }
-      cold_off[ci + 1] = cold_off[ci] + cold[ci].size();
-    }
-    const size_t need = cold_off[sizes.size()];
-    if (need > sg.cold_host_cap) {
-      if (sg.cold_host) cudaFreeHost(sg.cold_host);
-      sg.cold_host = nullptr;
-      sg.cold_host_cap = 0;
-      const size_t cap = need + need / 2 + 1024;
-      CK(cudaMallocHost((void **)&sg.cold_host, cap * 2 * PP_PREV_KEEP * sizeof(double)));
-      sg.cold_host_cap = cap;
-    }
-    for (int i = 0; i < kStreams; i++)
-      if (!sg.cold_idx[i]) {
-        CK(cudaMalloc((void **)&sg.cold_idx[i], (size_t)sg.cap * sizeof(int32_t)));
-        CK(cudaMalloc((void **)&sg.cold_pack[i],
-                      ((size_t)sg.cap / 4 + 1) * 2 * PP_PREV_KEEP * sizeof(double)));
-      }
-  }
+  // (Measured and dropped, profiles/bench_r2b_n1_{pitched,flat}_d2h.json: bringing down only the
+  // 40 new columns of a trajectory with a pitched copy — the 10 kept ones are the caller's own
+  // previous points — and filling the rest on the host moves 17 % fewer bytes but runs at
+  // 44.7 M frames/s against 52.3 M for whole rows: 320-byte rows are a poor DMA shape.)
   // Nothing may still be writing into the caller's buffers when this returns, whatever the
-  // outcome: a failure below joins the streams (and the fill threads) before it reports.
+  // outcome: a failure below joins the streams before it reports.
   struct Join {
     Staging &sg;
-    std::vector<std::thread> workers;
     ~Join() {
-      for (std::thread &t : workers) t.join();
       for (int i = 0; i < kStreams; i++)
         if (sg.streams[i]) cudaStreamSynchronize(sg.streams[i]);
       cudaGetLastError();
     }
-  } join_on_exit{sg, {}};
-  if (pitched) {
-    const int nt = n_frames >= 65536 ? host_threads() : 1;
-    double *hx = (double *)out->next_x, *hy = (double *)out->next_y;
-    auto fill = [=](int64_t a, int64_t b) {
-      for (int64_t f = a; f < b; f++)
-        if (in->prev_n[f] >= PP_PREV_KEEP) {
-          std::memcpy(hx + f * PP_PATH_LEN, in->prev_x + f * PP_PREV_KEEP, PP_PREV_KEEP * sizeof(double));
-          std::memcpy(hy + f * PP_PATH_LEN, in->prev_y + f * PP_PREV_KEEP, PP_PREV_KEEP * sizeof(double));
-        }
-    };
-    // (chunks that come down as whole rows are simply overwritten with the same values)
-    for (int t = 1; t < nt; t++)
-      join_on_exit.workers.emplace_back(fill, n_frames * t / nt, n_frames * (t + 1) / nt);
-    if (nt == 1) fill(0, n_frames);  // small batch: not worth a thread
-    else join_on_exit.workers.emplace_back(fill, (int64_t)0, n_frames / nt);
-  }
+  } join_on_exit{sg};
   int slot = 0;
   int64_t lo = 0;
   for (size_t ci = 0; ci < sizes.size(); lo += sizes[ci], ci++, slot = (slot + 1) % kStreams) {
@@ -616,43 +527,10 @@ extern "C" int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const
     if (rc != PP_OK) return rc;
     for (int i = 0; i < 23; i++) {
       if (!hout[i].p || hout[i].bpf == 0) continue;
-      if (i < 2 && !flat[ci]) {  // trajectories: the 40 columns that are new
-        const size_t head = PP_PREV_KEEP * sizeof(double), rowb = PP_PATH_LEN * sizeof(double);
-        CK(cudaMemcpy2DAsync((char *)hout[i].p + rowb * (size_t)lo + head, rowb,
-                             (const char *)dout[i] + head, rowb, rowb - head, (size_t)cnt,
-                             cudaMemcpyDeviceToHost, st));
-        continue;
-      }
       CK(cudaMemcpyAsync((char *)hout[i].p + hout[i].bpf * (size_t)lo, dout[i],
                          hout[i].bpf * (size_t)cnt, cudaMemcpyDeviceToHost, st));
     }
-    if (!flat[ci] && !cold[ci].empty()) {  // ... and the first 10 of the cold-start frames
-      const int count = (int)cold[ci].size();
-      CK(cudaMemcpyAsync(sg.cold_idx[slot], cold[ci].data(), count * sizeof(int32_t),
-                         cudaMemcpyHostToDevice, st));
-      k_gather_head<<<(count * PP_PREV_KEEP + 255) / 256, 256, 0, st>>>(
-          (const double *)dout[0], (const double *)dout[1], sg.cold_idx[slot], count,
-          sg.cold_pack[slot]);
-      ppi::count_launch();
-      CK(cudaMemcpyAsync(sg.cold_host + cold_off[ci] * 2 * PP_PREV_KEEP, sg.cold_pack[slot],
-                         (size_t)count * 2 * PP_PREV_KEEP * sizeof(double), cudaMemcpyDeviceToHost,
-                         st));
-    }
   }
   for (int i = 0; i < kStreams; i++) CK(cudaStreamSynchronize(sg.streams[i]));
-  if (pitched) {  // scatter the cold-start frames' first points
-    int64_t lo0 = 0;
-    for (size_t ci = 0; ci < sizes.size(); lo0 += sizes[ci], ci++) {
-      const size_t count = cold[ci].size();
-      const double *pk = sg.cold_host + cold_off[ci] * 2 * PP_PREV_KEEP;
-      for (size_t i = 0; i < count; i++) {
-        const int64_t f = lo0 + cold[ci][i];
-        std::memcpy((double *)out->next_x + f * PP_PATH_LEN, pk + i * PP_PREV_KEEP,
-                    PP_PREV_KEEP * sizeof(double));
-        std::memcpy((double *)out->next_y + f * PP_PATH_LEN, pk + (count + i) * PP_PREV_KEEP,
-                    PP_PREV_KEEP * sizeof(double));
-      }
-    }
-  }
   return PP_OK;
 }

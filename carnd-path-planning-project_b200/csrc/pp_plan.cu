@@ -365,13 +365,14 @@ PPD_INLINE void store_path_tail(const pp_plans &out, int64_t f, int np, uint32_t
 // ---------------------------------------------------------------------------
 // Stage D..I tail: decision, speed target, trajectory, outputs (one frame).
 // ---------------------------------------------------------------------------
+template <bool kLeanFirst = false>
 PPD_INLINE void stage_finish(const MapView &m, const pp_config &cfg, const pp_frames &in,
                              const pp_plans &out, int64_t f, const FrameCtx &c, const Behav &b,
                              int tl_in, uint32_t flags0) {
   const Decision d = stage_decide(cfg, in, out, f, c, b, tl_in, flags0);
   uint32_t flags = d.flags;
   // trajectory (:1446-1448)
-  const int np = build_trajectory(m, cfg, c.rs, in.prev_x + f * PP_PREV_KEEP,
+  const int np = build_trajectory<kLeanFirst>(m, cfg, c.rs, in.prev_x + f * PP_PREV_KEEP,
                                   in.prev_y + f * PP_PREV_KEEP, c.nprev, c.x, c.y,
                                   in.ego_yaw_deg[f], d.target_lane, c.d, c.vd, d.sc,
                                   out.next_x + f * PP_PATH_LEN, out.next_y + f * PP_PATH_LEN, flags);
@@ -472,7 +473,7 @@ PPD_INLINE void plan_one_frame_warp(const MapView &m, const pp_config &cfg, cons
   __syncwarp();
 #pragma unroll 1
   for (int o = 1; o < 32; o <<= 1) behav_merge_xor(b, flags, o);
-  stage_finish(m, cfg, in, out, f, c, b, tl_in, flags);
+  stage_finish<true>(m, cfg, in, out, f, c, b, tl_in, flags);
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -1747,11 +1748,14 @@ using ppi::offset_frames;
 using ppi::offset_plans;
 
 constexpr int64_t kPipeChunk = 1 << 18;  // frames per scratch buffer (≈ 155 MB at 12 cars)
-constexpr int64_t kFusedBelow = 4096;    // auto: batches this small go through the fused kernel
+constexpr int64_t kFusedBelow = 1536;    // auto: batches this small take the warp-per-frame kernel
+                                         // (profiles/r2_latency.log: 82 us at 1,024 frames against
+                                         // 124 us for the pipeline; 246 against 131 at 4,095)
 
 template <class K>
 int ensure_smem(K kernel, size_t smem) {
-  if (smem > 48 * 1024) {
+  // (the 48 KB default limit counts static shared memory too: k_cars has 2.5 KB of it)
+  if (smem > 40 * 1024) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
         cudaSuccess)
       return check_launch("cudaFuncSetAttribute");

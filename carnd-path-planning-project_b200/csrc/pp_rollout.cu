@@ -247,14 +247,20 @@ k_sim_advance(Track trk, int64_t lo, int64_t n, int c, uint64_t seed, int64_t fi
     const int ln = threadIdx.x & 31;
     const int64_t wr0 = r0 + (threadIdx.x & ~31);
     long long xs = 0;
-    for (int rr = 0; rr < 32; rr++) {
+    // the 32 rows are one contiguous run of 1,600 points: 50 coalesced trips, independent of
+    // each other (as a loop over rows every trip waited for the previous row's loads: 64
+    // dependent round trips to memory, a third of this kernel's 68 us)
+    const int64_t base = wr0 * PP_PATH_LEN;
+    const int64_t limit = (lo + n) * PP_PATH_LEN;
+#pragma unroll 10
+    for (int t = 0; t < PP_PATH_LEN; t++) {
+      const int e = t * 32 + ln;
+      const int rr = e / PP_PATH_LEN;
       const int np_r = __shfl_sync(0xffffffffu, np, rr);
-      const int64_t base = (wr0 + rr) * PP_PATH_LEN;
-      for (int i = ln; i < np_r; i += 32) {
-        const double x = pl.next_x[base + i], y = pl.next_y[base + i];
-        if (x == x && y == y && fabs(x) < 1e12 && fabs(y) < 1e12)
-          xs += (long long)(x * 256.0) + (long long)(y * 256.0);
-      }
+      const bool in = base + e < limit;
+      const double x = in ? pl.next_x[base + e] : 0.0, y = in ? pl.next_y[base + e] : 0.0;
+      if (in && e - rr * PP_PATH_LEN < np_r && x == x && y == y && fabs(x) < 1e12 && fabs(y) < 1e12)
+        xs += (long long)(x * 256.0) + (long long)(y * 256.0);
     }
     unsigned long long v = (unsigned long long)xs;
 #pragma unroll
@@ -484,7 +490,7 @@ int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStre
   // groups: contiguous ranges of rollouts (at least 4096 each, so that small jobs stay whole)
   static const int want_groups = [] {
     const char *e = getenv("PP_ROLLOUT_GROUPS");
-    const int v = e && *e ? atoi(e) : 4;
+    const int v = e && *e ? atoi(e) : 8;  // profiles/r2_rollouts.log: 4 groups 78-214 M, 8 groups 217 M every run
     return v < 1 ? 1 : (v > pp_rollouts::kGroups ? pp_rollouts::kGroups : v);
   }();
   int groups = want_groups;

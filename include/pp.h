@@ -264,7 +264,7 @@ int pp_plan_stats_batch(const pp_map *map, const pp_config *cfg, const pp_frames
                         const pp_plans *out, int64_t n_frames, int64_t *stats_dev,
                         void *cuda_stream);
 
-/* Kernel selection for pp_plan_batch: 0 = auto (the pipeline; below 4096 frames the
+/* Kernel selection for pp_plan_batch: 0 = auto (the pipeline; below 1536 frames the
  * warp-per-frame kernel), 1 = one thread per frame in a single kernel, 2 = the pipeline
  * (k_prep, k_cars, k_decide_t, k_emit), 3 = the pipeline with the tiled cars kernel (a warp's
  * frames' cars by TMA into shared memory, reductions in the same kernel), 4 = one warp per

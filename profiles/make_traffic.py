@@ -1,8 +1,11 @@
-"""profiles/traffic.json + per-kernel text summaries from an ncu --set full report.
-    python profiles/make_traffic.py gpurun_out/prof_r1d.ncu-rep r1d 262144
-"""
+"""profiles/traffic*.json + per-kernel text summaries from an ncu --set full report.
+    python profiles/make_traffic.py gpurun_out/prof_r2.ncu-rep r2 262144 [cars] [out.json]
+(cars defaults to 12 and the output to traffic.json; bench.py reads traffic.json for 12 cars and
+traffic_c<cars>.json otherwise)"""
 import csv, io, json, os, re, subprocess, sys
 rep, tag, frames = sys.argv[1], sys.argv[2], int(sys.argv[3])
+cars = int(sys.argv[4]) if len(sys.argv) > 4 else 12
+out_name = sys.argv[5] if len(sys.argv) > 5 else ("traffic.json" if cars == 12 else f"traffic_c{cars}.json")
 here = os.path.dirname(os.path.abspath(__file__))
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -13,7 +16,9 @@ def num(r, k):
     return float(r[col[k]].replace(",", "") or 0)
 traffic, times, fp64, issue, lanes = {}, {}, {}, {}, {}
 for i, r in enumerate(rows[2:]):
-    name = re.search(r"(k_\w+|stats_kernel|plan_fused)", r[col["Kernel Name"]]).group(1)
+    name = re.search(r"(k_\w+|f?stats_kernel|plan_fused|plan_warp)", r[col["Kernel Name"]]).group(1)
+    if name in traffic:  # a second launch of the same kernel: keep the first
+        continue
     rd = num(r, "dram__bytes_read.sum") * scale[units[col["dram__bytes_read.sum"]]]
     wr = num(r, "dram__bytes_write.sum") * scale[units[col["dram__bytes_write.sum"]]]
     traffic[name] = rd + wr
@@ -26,10 +31,10 @@ for i, r in enumerate(rows[2:]):
     open(os.path.join(here, f"{tag}_{name}_ncu.txt"), "w").write(txt)
 pipe = {k: v for k, v in traffic.items() if k != "stats_kernel"}
 json.dump({"source": f"profiles/{tag}_*_ncu.txt: ncu --set full --clock-control none, one launch of each "
-                     f"kernel over {frames} frames x 12 cars on a gpurun B200",
-           "frames_per_launch": frames, "dram_bytes_per_launch": pipe,
+                     f"kernel over {frames} frames x {cars} cars on a gpurun B200",
+           "frames_per_launch": frames, "cars_per_frame": cars, "dram_bytes_per_launch": pipe,
            "stats_kernel_dram_bytes_per_launch": traffic.get("stats_kernel"),
            "gpu_time_us_under_ncu": times,
            "fp64_pipe_active_pct": fp64, "issue_active_pct": issue, "active_lanes_per_warp_instr": lanes},
-          open(os.path.join(here, "traffic.json"), "w"), indent=1)
+          open(os.path.join(here, out_name), "w"), indent=1)
 print(json.dumps(traffic), sum(pipe.values()) / frames, "B/frame")

@@ -224,10 +224,8 @@ def test_ragged_and_edge_inputs(pp, torch_cuda, gmap, oracle):
 
 @pytest.mark.parametrize("cold", ["few", "some", "most"])
 def test_host_entry_point_equals_device_entry_point(pp, torch_cuda, gmap, cold):
-    """pp_plan_batch_host (copies + chunk pipeline inside) == pp_plan_batch.  The host entry
-    point brings down only the 40 new columns of a trajectory and fills the 10 kept ones from
-    the caller's previous points; cold-start frames (every column new) come down packed, chunks
-    that are mostly cold as whole rows: all three routes."""
+    """pp_plan_batch_host (copies + chunk pipeline inside) == pp_plan_batch, with few, some and
+    mostly cold-start frames; a second call over stale host buffers gives the same."""
     n = 150000  # > 2 chunks of 65536, ragged tail
     fb = pp.synth_frames(gmap, n, 12, seed=41)
     rng = np.random.default_rng(41)
