@@ -186,6 +186,10 @@ k_sweep_emit(const __grid_constant__ pp_config cfg, const __grid_constant__ pp_f
     flags = 0;
     traj_emit(kn, cfg, sc, s_head[3], s_head[4], s_head[5], s_head[6], np, so, flags, bail);
   }
+  // (bail 1 — a spline argument at or left of the first staged knot, which lies LEFT of the
+  // local origin — needs the loop to walk backwards, i.e. a negative speed.  A candidate's ramp
+  // runs from the ego speed (a norm, >= 0) to v_i >= 0 and acceleration overrides only cap
+  // increases, so no candidate gets there; were it to happen it would be scored BAD here.)
   *dst = bail ? PP_SWEEP_BAD : so.score(cfg, lane, target_lane[f]);
 }
 

@@ -81,9 +81,16 @@ static int ppref_printf(const char *fmt, ...) {
   va_end(ap);
   return 0;
 }
+static FILE *g_tee = NULL;  // ppref_plan_frames_log: the reference's log text goes here as well
 static int ppref_fprintf(FILE *, const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
+  if (g_tee) {
+    va_list ap2;
+    va_copy(ap2, ap);
+    vfprintf(g_tee, fmt, ap2);
+    va_end(ap2);
+  }
   classify(fmt, ap);
   va_end(ap);
   return 0;
@@ -362,6 +369,7 @@ int ppref_plan_frames_log(ppref_map *m, const pp_frames *in, const pp_plans *out
   FILE *f = fopen(log_path, "wt");
   if (!f) return PP_E_IO;
   fLog = f;
+  g_tee = f;
   Map local = m->map;
   for (int64_t i = 0; i < n; i++) {
     t_flags = 0;
@@ -370,6 +378,7 @@ int ppref_plan_frames_log(ppref_map *m, const pp_frames *in, const pp_plans *out
     if (out->flags) out->flags[i] = t_flags;
   }
   fLog = NULL;
+  g_tee = NULL;
   fclose(f);
   return PP_OK;
 }
