@@ -610,7 +610,7 @@ extern "C" int pp_rollouts_run(pp_rollouts *r, const pp_config *cfg, int64_t n_t
   for (int64_t t = 0; t < n_ticks; t++) {
     const int rc = issue_tick(r, cfg, consume_k, st, t == 0, t == n_ticks - 1);
     if (rc != PP_OK) {
-      if (t > 0) issue_join_only(r, st);  // keep `st` ordered after what was already issued
+      issue_join_only(r, st);  // keep `st` ordered after whatever the group streams were given
       return rc;
     }
     r->tick++;
