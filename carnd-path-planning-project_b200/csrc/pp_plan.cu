@@ -13,13 +13,15 @@
 //   k_cars     one thread per CAR   : Map::lane_matching + project_speed for
 //              every sensor-fusion object (:1325-1350); warp tiles of 256 cars
 //              counting-sorted by expected walk length
-//   k_decide   one thread per FRAME : LaneChangePlanner reductions, veto,
-//              followed cars, LimitSpeed, SpeedController (:1352-1438),
-//              TrajectoryBuilder set-up and the tk::spline fit (:565-904)
+//   k_decide_t one thread per FRAME, tiles of 128 : LaneChangePlanner reductions,
+//              veto, followed cars, LimitSpeed, SpeedController (:1352-1438),
+//              TrajectoryBuilder set-up and the tk::spline fit (:565-904); the
+//              tile's previous points come in by TMA bulk copies, the kept
+//              points of the result leave by bulk stores from the same tile
 //   k_emit     one thread per FRAME : the 0.02 s point emission loop
 //              (:904-1040) on the <= 7 reachable knots staged in shared memory
 //   k_fallback dense, side stream   : the angle-based generator (:848-901) for
-//              the frames k_decide queued (~0.4 %)
+//              the frames k_decide_t queued (~0.4 %)
 //   k_slow     warp per frame, side : the complete path for frames k_emit gave
 //              up on (headings / rotations outside its fast forms, ~0.03 %)
 //
@@ -27,10 +29,13 @@
 // double-buffered, stream-ordered scratch in HBM.  The ncu evidence behind each
 // cut is in profiles/ (r1_v0: the single fused kernel, 45 % instruction-fetch
 // stalls on 155 KB of SASS at 15 of 32 lanes; r1b/r1c: the division of the
-// interior step at 4 lanes, the library atan2 at 3.6 lanes, knot staging; r1j:
-// the current state).  The fused single-kernel form is kept as variant 1: it
-// has the lowest latency for small batches and is the bitwise cross-check of
-// the pipeline (tests/test_gpu_parity.py).
+// interior step at 4 lanes, the library atan2 at 3.6 lanes, knot staging; r2:
+// the current state and the tile experiments of DESIGN.md §3.1).  Other forms of
+// the same step, all bit-identical (tests/test_gpu_parity.py): variant 1, one
+// thread per frame in one kernel (the cross-check); variant 3, k_cars_t (a
+// warp's frames' cars by TMA into shared memory, reductions in the same kernel:
+// half the DRAM traffic, 7 % slower); variant 4, plan_warp, one warp per frame
+// (the default below 1,536 frames: 51 us for one frame).
 #include <cuda_runtime.h>
 
 #include <atomic>
