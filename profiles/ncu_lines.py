@@ -2,6 +2,8 @@
 source line / per device function.
 
     python profiles/ncu_lines.py gpurun_out/prof.ncu-rep <kernel-substring> [top]
+    PP_SECTION=<mangled-substring> ... when the demangled name ncu shows ("k_decide_t<0>")
+    and the ELF section name (".text._ZN..10k_decide_tILb0EEE...") need different substrings
 
 Needs ncu, cuobjdump, nvdisasm (CPU box is fine) and the libpp_b200.so the
 report was captured from (built with -lineinfo).
@@ -25,7 +27,7 @@ for f in os.listdir(tmp):
         if ln.startswith(".text."):
             # the first matching section only: template instances (k_emit<PairOut>, <ArrayOut>)
             # share a name and their offsets would overwrite each other
-            inside = (kern in ln) and not matched
+            inside = (os.environ.get("PP_SECTION", kern) in ln) and not matched
             matched = matched or inside
             cur = None
         if not inside:
