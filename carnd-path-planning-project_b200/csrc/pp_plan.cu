@@ -663,12 +663,18 @@ k_prep(const double *__restrict__ map_table, int n_wp, const __grid_constant__ p
 #ifndef PP_TILE_K
 #define PP_TILE_K 8
 #endif
-constexpr int kTileK = PP_TILE_K;      // cars per lane per tile
-constexpr int kTile = 32 * kTileK;     // car slots per tile
+// kTileK = cars per lane per tile (a tile is 32 kTileK car slots).  8 is the throughput setting
+// (profiles/r2_tilek.log: 4 -> 1.01 ms, 8 -> 0.97, 16 -> 1.21 per 1M frames); a chunk too small to
+// give every resident warp a tile of 256 takes tiles of 64, which spreads it over four times as
+// many warps and quarters the kernel's latency (closed-loop rollouts tick in chunks of 8,192
+// frames: their chain of dependent launches is what bounds them).
+constexpr int kTileKBig = PP_TILE_K, kTileKSmall = 2;
 constexpr int kBins = 24;              // proxy bins; bin kBins = slot holds no car
+template <int kTileK>
 __global__ void __launch_bounds__(kBlock, PP_CARS_MINB)
 k_cars(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_frames in,
        const __grid_constant__ pp_plans out, const __grid_constant__ Scratch sc, int64_t n) {
+  constexpr int kTile = 32 * kTileK;  // car slots per tile
   extern __shared__ __align__(16) double s_map[];
   __shared__ int s_hist[kBlock / 32][32];
   __shared__ unsigned short s_order[kBlock / 32][kTile];
@@ -1856,7 +1862,8 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
   if ((rc = ensure_smem(plan_fused, smem)) != PP_OK) return rc;
   if ((rc = ensure_smem(plan_warp, smem)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_prep, smem)) != PP_OK) return rc;
-  if ((rc = ensure_smem(k_cars, smem)) != PP_OK) return rc;
+  if ((rc = ensure_smem(k_cars<kTileKBig>, smem)) != PP_OK) return rc;
+  if ((rc = ensure_smem(k_cars<kTileKSmall>, smem)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_slow, smem)) != PP_OK) return rc;
   const size_t smem_emit = (size_t)5 * PPD_TAILK * kBlock * sizeof(double);
   if ((rc = ensure_smem(k_emit<ArrayOut, false>, smem_emit)) != PP_OK) return rc;
@@ -2043,9 +2050,16 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     }
     k_prep<<<grid_for(cnt, prep_blocks), kBlock, smem, ls>>>(map->dev_table, map->n, *cfg, fin, sc, cnt);
     phase_mark(pe, 1, ls);
-    if (mc > 0)
-      k_cars<<<grid_for((cnt * mc + kTileK - 1) / kTileK, cars_blocks), kBlock, smem, ls>>>(
-          map->dev_table, map->n, fin, fout, sc, cnt);
+    if (mc > 0) {
+      // (a resident warp per tile of 256: 148 SMs x 6 blocks x 4 warps)
+      const bool small = cnt * mc < (int64_t)sm_count() * 6 * 4 * 32 * kTileKBig;
+      if (small)
+        k_cars<kTileKSmall><<<grid_for((cnt * mc + kTileKSmall - 1) / kTileKSmall, cars_blocks), kBlock,
+                              smem, ls>>>(map->dev_table, map->n, fin, fout, sc, cnt);
+      else
+        k_cars<kTileKBig><<<grid_for((cnt * mc + kTileKBig - 1) / kTileKBig, cars_blocks), kBlock, smem,
+                            ls>>>(map->dev_table, map->n, fin, fout, sc, cnt);
+    }
     phase_mark(pe, 2, ls);
     k_decide_t<false><<<grid_for(cnt, decide_blocks), kBlock, smem_tile, ls>>>(
         map->dev_table, map->n, *cfg, fin, fout, sc, cnt, bulk_prev,
