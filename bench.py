@@ -388,6 +388,7 @@ def single_rank_stats(pp, m, world, n, cars, first_of_rank, torch, df, dp):
     """The statistics of all ranks' shards planned on THIS device alone (the N-rank reduced
     vector must equal it bit for bit): shards generated in HBM one after the other, into the
     rank's own buffers (df / dp are overwritten; the last shard generated is rank 0's again)."""
+    from carnd_path_planning_project_b200 import parallel
     tot_i = torch.zeros(pp.STATS_LEN, dtype=torch.int64, device="cuda")
     tot_f = None
     for r in list(range(1, world)) + [0]:
@@ -395,11 +396,7 @@ def single_rank_stats(pp, m, world, n, cars, first_of_rank, torch, df, dp):
         st = pp.plan_stats_batch(m, df, dp)
         fs = pp.fstats_batch(dp)
         tot_i += st
-        if tot_f is None:
-            tot_f = fs.clone()
-        else:
-            tot_f[:pp.FSTAT_NMIN] = torch.minimum(tot_f[:pp.FSTAT_NMIN], fs[:pp.FSTAT_NMIN])
-            tot_f[pp.FSTAT_NMIN:] = torch.maximum(tot_f[pp.FSTAT_NMIN:], fs[pp.FSTAT_NMIN:])
+        tot_f = fs.clone() if tot_f is None else parallel.merge_fstats(tot_f, fs, pp.FSTAT_NMIN)
     torch.cuda.synchronize()
     return tot_i, tot_f
 

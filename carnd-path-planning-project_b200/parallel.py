@@ -2,10 +2,12 @@
 
 Frames are independent, so the batch is cut into contiguous shards (one per
 rank, one process per GPU) and planned with no data-path collective.  The only
-exchange is a sum all-reduce of the int64 statistics vector produced by
-pp_stats_batch (exact integer sums, so 1/2/4/8-rank results are identical).
-torch.distributed is the transport: NCCL for CUDA tensors, gloo in the CPU
-tests.
+exchange is the final reduction of the statistics: a sum of the int64 vector of
+pp_stats_batch (exact integer sums, so 1/2/4/8-rank results are identical) and
+a min / max of the f64 vector of pp_fstats_batch.  On GPUs that reduction is
+pp_stats_reduce in the C library (NCCL); the functions below are the same rules
+over torch.distributed (gloo in the CPU tests) and on single vectors (the
+N-rank == 1-rank check of bench.py).
 """
 from __future__ import annotations
 
@@ -26,3 +28,33 @@ def allreduce_stats(stats):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
     return stats
+
+
+def merge_fstats(a, b, n_min: int):
+    """The reduction rule of the f64 statistics (pp.h, PP_FSTAT_*): element-wise minimum over
+    the first n_min entries, maximum over the rest.  Works on torch tensors and numpy arrays."""
+    import numpy as np
+    if isinstance(a, np.ndarray):
+        out = a.copy()
+        out[:n_min] = np.minimum(a[:n_min], b[:n_min])
+        out[n_min:] = np.maximum(a[n_min:], b[n_min:])
+        return out
+    import torch
+    out = a.clone()
+    out[:n_min] = torch.minimum(a[:n_min], b[:n_min])
+    out[n_min:] = torch.maximum(a[n_min:], b[n_min:])
+    return out
+
+
+def allreduce_fstats(fstats, n_min: int):
+    """In-place MIN / MAX all-reduce of an f64 statistics tensor over the default process group
+    (what pp_stats_reduce does with ncclMin / ncclMax)."""
+    import torch
+    import torch.distributed as dist
+    assert fstats.dtype == torch.float64
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        lo, hi = fstats[:n_min].clone(), fstats[n_min:].clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        fstats[:n_min], fstats[n_min:] = lo, hi
+    return fstats

@@ -32,6 +32,30 @@ def numpy_stats(abi, plans):
     return st
 
 
+def numpy_fstats(abi, plans):
+    """Mirror of pp_fstats_batch (definition in include/pp.h) for host-side plans."""
+    x, y, npts = plans.next_x, plans.next_y, plans.n_points
+    out = np.array([np.inf] * abi.FSTAT_NMIN + [-np.inf] * (abi.FSTATS_LEN - abi.FSTAT_NMIN))
+
+    def upd(i, vals):
+        vals = vals[np.isfinite(vals)]
+        if len(vals):
+            out[i] = min(out[i], vals.min()) if i < abi.FSTAT_NMIN else max(out[i], vals.max())
+    upd(0, plans.ego_speed), upd(3, plans.ego_speed)
+    upd(1, plans.target_speed), upd(4, plans.target_speed)
+    with np.errstate(invalid="ignore", over="ignore"):
+        vx, vy = (x[:, 1:] - x[:, :-1]) * 50, (y[:, 1:] - y[:, :-1]) * 50
+        sp = np.sqrt(vx * vx + vy * vy)
+        k = np.arange(sp.shape[1])[None, :]
+        live = sp[k < (npts[:, None] - 1)]
+        upd(2, live), upd(5, live)
+        ax, ay = (vx[:, 1:] - vx[:, :-1]) * 50, (vy[:, 1:] - vy[:, :-1]) * 50
+        acc = np.sqrt(ax * ax + ay * ay)
+        k = np.arange(acc.shape[1])[None, :]
+        upd(6, acc[k < (npts[:, None] - 2)])
+    return out
+
+
 def _worker(rank, world, port, n_total, q):
     sys.path.insert(0, HERE)
     import torch
@@ -47,7 +71,9 @@ def _worker(rank, world, port, n_total, q):
     plans = checkers.Checker("oracle").plan(frames, cars=False)
     st = torch.from_numpy(numpy_stats(checkers.abi, plans))
     parallel.allreduce_stats(st)
-    q.put((rank, lo, hi, st.numpy().copy(), plans.target_lane.copy()))
+    fs = torch.from_numpy(numpy_fstats(checkers.abi, plans))
+    parallel.allreduce_fstats(fs, checkers.abi.FSTAT_NMIN)  # what pp_stats_reduce does on GPUs
+    q.put((rank, lo, hi, st.numpy().copy(), plans.target_lane.copy(), fs.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -71,8 +97,11 @@ def test_two_rank_shards_reduce_to_the_single_rank_result(pp, pmap, oracle, abi)
     whole = oracle.plan(whole_frames, cars=False)
     want = numpy_stats(abi, whole)
     assert results[0][1:3] == (0, 1500) and results[1][1:3] == (1500, 3001)
+    want_f = numpy_fstats(abi, whole)
     for r in results:
         assert np.array_equal(r[3], want)  # every rank holds the global sums
+        assert np.array_equal(r[5], want_f)  # ... and the global minima / maxima, bit for bit
+    assert np.isfinite(want_f).all() and want_f[abi.FSTAT_NMIN + 3] > 0
     assert np.array_equal(np.concatenate([r[4] for r in results]), whole.target_lane)
     assert want[abi.STAT_FRAMES] == n_total and want[abi.STAT_POINTS] > 0
 
@@ -87,3 +116,13 @@ def test_shard_range_partitions_exactly(pp):
             assert max(hi - lo for lo, hi in edges) - min(hi - lo for lo, hi in edges) <= 1
     with pytest.raises(ValueError):
         parallel.shard_range(10, 2, 2)
+
+
+def test_merge_fstats_rule(pp, abi):
+    from carnd_path_planning_project_b200 import parallel
+    a = np.array([1.0, 2.0, 3.0, 10.0, 20.0, 30.0, 40.0])
+    b = np.array([0.5, 9.0, 3.0, 11.0, 5.0, 30.0, 41.0])
+    got = parallel.merge_fstats(a, b, abi.FSTAT_NMIN)
+    assert list(got) == [0.5, 2.0, 3.0, 11.0, 20.0, 30.0, 41.0]
+    ident = np.array([np.inf] * abi.FSTAT_NMIN + [-np.inf] * (abi.FSTATS_LEN - abi.FSTAT_NMIN))
+    assert np.array_equal(parallel.merge_fstats(a, ident, abi.FSTAT_NMIN), a)
