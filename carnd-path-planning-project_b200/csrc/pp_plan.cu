@@ -36,11 +36,13 @@
 // warp's frames' cars by TMA into shared memory, reductions in the same kernel:
 // half the DRAM traffic, 7 % slower); variant 4, plan_warp, one warp per frame
 // (the default below 1,536 frames: 51 us for one frame).
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through the runtime)
 #include <cuda_runtime.h>
 
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -1280,8 +1282,14 @@ template <bool kBehav>
 __global__ void __launch_bounds__(kBlock, PP_DECIDE_MINB)
 k_decide_t(const double *__restrict__ map_table, int n_wp, const __grid_constant__ pp_config cfg,
            const __grid_constant__ pp_frames in, const __grid_constant__ pp_plans out,
-           const __grid_constant__ Scratch sc, int64_t n, int bulk_in, int bulk_out) {
-  extern __shared__ __align__(16) double s_dyn[];
+           const __grid_constant__ Scratch sc, int64_t n, int bulk_in, int bulk_out,
+           const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y) {
+  // bulk_out: 0 = the kept points go out by ordinary stores, 1 = one 80-byte bulk copy per lane
+  // and coordinate, 2 = ONE 2-D tensor-map store per tile and coordinate (tm_x / tm_y describe
+  // next_x / next_y of this chunk as [n][50] with a box of [128 rows][10 columns]; a tensor
+  // copy wants its shared-memory side on a 128-byte boundary: s_px / s_py are at 35,840 and
+  // 46,080 bytes of a 128-byte aligned array)
+  extern __shared__ __align__(128) double s_dyn[];
   double *s_rows = s_dyn;                                      // [PPD_SWEEP_ROWS * PPD_TAILK][kBlock]
   double *s_px = s_dyn + PPD_SWEEP_ROWS * PPD_TAILK * kBlock;  // [kBlock][10]
   double *s_py = s_px + kBlock * PP_PREV_KEEP;
@@ -1331,13 +1339,23 @@ k_decide_t(const double *__restrict__ map_table, int n_wp, const __grid_constant
       }
       __syncthreads();
     }
+    if (bulk_out == 2 && threadIdx.x == 0) {
+      // result_points = prev_trajectory (:578) for the whole tile at once: columns [0, 10) of
+      // rows f0 .. f0 + 127 (rows past the chunk are clipped by the tensor map).  A frame
+      // WITHOUT a previous path gets its stale input row here; every one of its 50 columns is
+      // written afterwards by the kernel that emits its points (k_emit / k_fallback / k_slow).
+      fence_async_smem();
+      tensor_s2g_2d(&tm_x, 0, (int)f0, smem_addr(s_px));
+      tensor_s2g_2d(&tm_y, 0, (int)f0, smem_addr(s_py));
+      bulk_commit();
+    }
     if (own) {
       const double *px = s_px + threadIdx.x * PP_PREV_KEEP;
       const double *py = s_py + threadIdx.x * PP_PREV_KEEP;
       uint32_t flags = d.flags;
       double *gx = out.next_x + f * PP_PATH_LEN, *gy = out.next_y + f * PP_PATH_LEN;
       if (c.nprev) {  // result_points = prev_trajectory (:578): straight from the staged tile
-        if (bulk_out) {
+        if (bulk_out == 1) {
           bulk_s2g(gx, smem_addr(px), PP_PREV_KEEP * 8);
           bulk_s2g(gy, smem_addr(py), PP_PREV_KEEP * 8);
           bulk_commit();
@@ -1381,8 +1399,9 @@ k_decide_t(const double *__restrict__ map_table, int n_wp, const __grid_constant
         sc.e_nk[f] = cnt | (r0 > 0 ? kEstPartial : 0);
         sc.e_flags[f] = flags;
       }
-      if (bulk_out) bulk_wait_read();  // the tile is overwritten by the next load
+      if (bulk_out == 1) bulk_wait_read();  // the tile is overwritten by the next load
     }
+    if (bulk_out == 2 && threadIdx.x == 0) bulk_wait_read();
     fence_async_smem();
     __syncthreads();
   }
@@ -1763,6 +1782,57 @@ constexpr int64_t kFusedBelow = 1536;    // auto: batches this small take the wa
                                          // (profiles/r2_latency.log: 82 us at 1,024 frames against
                                          // 124 us for the pipeline; 246 against 131 at 4,095)
 
+// 2-D tensor map of a plan array [rows][50] of doubles with a box of [kBlock rows][10 columns]
+// (the kept points of a k_decide_t tile).  The encoder lives in the driver library; it is
+// fetched through the runtime, so nothing links against libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_encoder() {
+  static const EncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+bool kept_points_map(CUtensorMap &tm, double *base, int64_t rows) {
+  // (a closed-loop run asks for the same few (array, rows) pairs every tick: keep the last ones)
+  struct Entry {
+    double *base = nullptr;
+    int64_t rows = 0;
+    CUtensorMap tm;
+  };
+  constexpr int kKeep = 32;
+  thread_local Entry cache[kKeep];
+  thread_local int next = 0;
+  for (int i = 0; i < kKeep; i++)
+    if (cache[i].base == base && cache[i].rows == rows) {
+      tm = cache[i].tm;
+      return true;
+    }
+  const EncodeTiledFn enc = tensor_encoder();
+  if (!enc || rows <= 0) return false;
+  const cuuint64_t gdim[2] = {PP_PATH_LEN, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {PP_PATH_LEN * sizeof(double)};
+  const cuuint32_t box[2] = {PP_PREV_KEEP, kBlock};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  cache[next].base = base;
+  cache[next].rows = rows;
+  cache[next].tm = tm;
+  next = (next + 1) % kKeep;
+  return true;
+}
+
 template <class K>
 int ensure_smem(K kernel, size_t smem) {
   // (the 48 KB default limit counts static shared memory too: k_cars has 2.5 KB of it)
@@ -1879,7 +1949,9 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
   if ((rc = ensure_smem(k_decide_t<false>, smem_tile)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_decide_t<true>, smem_tile)) != PP_OK) return rc;
   if ((rc = ensure_smem(k_slow_t, smem)) != PP_OK) return rc;
-  static const int decide_bulk_out = env_int("PP_DECIDE_BULK_OUT", 1, 0, 1);  // experiments
+  // kept points out of k_decide_t: 2 = one tensor-map store per tile, 1 = a bulk copy per lane,
+  // 0 = ordinary stores (experiments; unaligned rows always take 0)
+  static const int decide_bulk_out = env_int("PP_DECIDE_BULK_OUT", 2, 0, 2);
   // persistent grids: blocks per SM each kernel may occupy (a smaller share leaves room for the
   // kernels of the other chunks in flight; profiles/r2_grids.log)
   static const int decide_blocks = env_int("PP_DECIDE_BLOCKS", 4, 1, 16);
@@ -1992,6 +2064,14 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     sc.slow_nb = n_base + 2 * ci + 1;
     sc.dbg = dbg ? n_base + 2 * n_chunks : nullptr;
     sc.xsum = stats_dev ? (unsigned long long *)stats_dev + PP_STAT_XSUM : nullptr;
+    // how the kept points leave k_decide_t (see there); the tensor maps describe THIS chunk's rows
+    CUtensorMap tm_x, tm_y;
+    std::memset(&tm_x, 0, sizeof tm_x);
+    std::memset(&tm_y, 0, sizeof tm_y);
+    int bulk_out = paired ? decide_bulk_out : 0;
+    if (bulk_out == 2 &&
+        !(kept_points_map(tm_x, fout.next_x, cnt) && kept_points_map(tm_y, fout.next_y, cnt)))
+      bulk_out = 1;
     // the side stream may still be reading this pipe's scratch for its previous chunk
     if (ci >= pipes) cudaStreamWaitEvent(ls, side.ev_done, 0);
     pe = phase_begin(pe_store) ? &pe_store : nullptr;
@@ -2013,8 +2093,7 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
       }
       phase_mark(pe, 2, ls);
       k_decide_t<true><<<grid_for(cnt, decide_blocks), kBlock, smem_tile, ls>>>(
-          map->dev_table, map->n, *cfg, fin, fout, sc, cnt, bulk_prev,
-          paired && decide_bulk_out ? 1 : 0);
+          map->dev_table, map->n, *cfg, fin, fout, sc, cnt, bulk_prev, bulk_out, tm_x, tm_y);
       phase_mark(pe, 3, ls);
       cudaEventRecord(side.ev_a, ls);
       cudaStreamWaitEvent(side.st, side.ev_a, 0);
@@ -2062,8 +2141,7 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     }
     phase_mark(pe, 2, ls);
     k_decide_t<false><<<grid_for(cnt, decide_blocks), kBlock, smem_tile, ls>>>(
-        map->dev_table, map->n, *cfg, fin, fout, sc, cnt, bulk_prev,
-        paired && decide_bulk_out ? 1 : 0);
+        map->dev_table, map->n, *cfg, fin, fout, sc, cnt, bulk_prev, bulk_out, tm_x, tm_y);
     phase_mark(pe, 3, ls);
     // side stream: the frames k_decide queued, concurrently with k_emit and the next chunk
     cudaEventRecord(side.ev_a, ls);
