@@ -33,7 +33,7 @@ MAP_CSV = os.path.join(ROOT, "data", "highway_map.csv")
 EXPORTS = [
     "pp_version", "pp_init", "pp_strerror", "pp_last_cuda_error", "pp_device_count", "pp_config_default",
     "pp_map_create", "pp_map_create_from_csv", "pp_map_destroy", "pp_map_num_waypoints",
-    "pp_map_table", "pp_plan_batch", "pp_plan_batch_host", "pp_stats_batch",
+    "pp_map_table", "pp_plan_batch", "pp_plan_batch_host", "pp_plan_batch_host_split", "pp_stats_batch",
     "pp_set_kernel_variant", "pp_launch_count", "pp_distancesq_pt_seg_batch",
     "pp_init_reference_waypoint_batch", "pp_lane_matching_batch", "pp_get_lane_pos_batch",
     "pp_spline_batch", "pp_closest_waypoint_batch", "pp_next_waypoint_batch",
@@ -41,7 +41,7 @@ EXPORTS = [
     "pp_lane_change_batch", "pp_limit_speed_batch", "pp_trajectory_build_batch",
     "pp_set_phase_timing", "pp_get_phase_ms", "pp_speed_controller_batch",
     "pp_project_speed_batch", "pp_control_points_batch",
-    "pp_dev_alloc", "pp_dev_free", "pp_dev_upload", "pp_dev_download", "pp_dev_sync",
+    "pp_dev_alloc", "pp_dev_free", "pp_host_alloc", "pp_host_free", "pp_dev_upload", "pp_dev_download", "pp_dev_sync",
     "pp_dev_set", "pp_stream_create", "pp_stream_sync", "pp_stream_destroy",
     "pp_rollouts_create", "pp_rollouts_destroy", "pp_rollouts_run", "pp_rollouts_last",
     "pp_rollouts_get_state", "pp_rollouts_stats", "pp_rollouts_set_lean", "pp_sweep_batch",
@@ -170,6 +170,54 @@ def plan_batch_host(m: Map, frames: FrameBatch, plans: PlanBatch | None = None,
     fs, ps = frames.struct(), plans.struct()
     _check(lib.pp_plan_batch_host(m.handle, C.byref(cfg), C.byref(fs), C.byref(ps),
                                   C.c_int64(frames.n)), "pp_plan_batch_host")
+    return plans
+
+
+class _Pinned:
+    """Owner of one pp_host_alloc block."""
+
+    def __init__(self, nbytes: int):
+        self.p = C.c_void_p()
+        _check(lib.pp_host_alloc(C.byref(self.p), C.c_size_t(nbytes)), "pp_host_alloc")
+
+    def __del__(self):
+        try:
+            if self.p:
+                lib.pp_host_free(self.p)
+                self.p = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array in page-locked host memory (pp_host_alloc); freed with its last view."""
+    dt = np.dtype(dtype)
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    owner = _Pinned(max(nbytes, 1))
+    buf = (C.c_char * max(nbytes, 1)).from_address(owner.p.value)
+    buf._owner = owner  # the array's base keeps the block alive
+    return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+
+
+def pinned_like(a: np.ndarray) -> np.ndarray:
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
+
+
+def plan_batch_host_split(m: Map, frames: FrameBatch, plans: PlanBatch, head_x, head_y, tail_x,
+                          tail_y, cfg: Config | None = None) -> PlanBatch:
+    """pp_plan_batch_host_split: as plan_batch_host, but the trajectories come back as
+    head[n][PREV_KEEP] (written only for frames that kept no previous points; may be the
+    frames' own prev_x / prev_y arrays) and tail[n][PATH_LEN - PREV_KEEP]; `plans` must have
+    next_x = next_y = None."""
+    cfg = cfg or default_config()
+    fs, ps = frames.struct(), plans.struct()
+    rows = abi.SplitRows(_ptr(head_x), _ptr(head_y), _ptr(tail_x), _ptr(tail_y))
+    _check(lib.pp_plan_batch_host_split(m.handle, C.byref(cfg), C.byref(fs), C.byref(ps),
+                                        C.byref(rows), C.c_int64(frames.n)),
+           "pp_plan_batch_host_split")
     return plans
 
 

@@ -125,6 +125,11 @@ class Plans(C.Structure):
     _fields_ = [(n, _dp) for n, _, _ in PLAN_FIELDS]
 
 
+class SplitRows(C.Structure):
+    """pp_split_rows (pp_plan_batch_host_split): [n][PREV_KEEP] heads, [n][PATH_LEN - PREV_KEEP] tails."""
+    _fields_ = [(n, _dp) for n in ("head_x", "head_y", "tail_x", "tail_y")]
+
+
 SWEEP_LANES, SWEEP_SPEEDS, SWEEP_TIMES = 3, 16, 8
 SWEEP_CANDS = SWEEP_LANES * SWEEP_SPEEDS * SWEEP_TIMES
 SWEEP_BAD = 1e9

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "pp_internal.h"
 
@@ -246,6 +247,16 @@ int pp_dev_free(void *p) {
   if (p) PP_CK(cudaFree(p), "pp_dev_free");
   return PP_OK;
 }
+int pp_host_alloc(void **out, size_t bytes) {
+  if (!out) return PP_E_ARG;
+  *out = nullptr;
+  PP_CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault), "pp_host_alloc");
+  return PP_OK;
+}
+int pp_host_free(void *p) {
+  if (p) PP_CK(cudaFreeHost(p), "pp_host_free");
+  return PP_OK;
+}
 int pp_dev_upload(void *dst_dev, const void *src_host, size_t bytes) {
   if (bytes && (!dst_dev || !src_host)) return PP_E_ARG;
   if (bytes) PP_CK(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice), "pp_dev_upload");
@@ -342,7 +353,23 @@ struct Staging {
   char *in_buf[kStreams] = {};
   char *out_buf[kStreams] = {};
   size_t in_bytes = 0, out_bytes = 0;
+  // split rows (pp_plan_batch_host_split): per slot the compact tails [cap][40] x, y; mapped
+  // pinned host blocks for the list of frames without kept points and their heads [.][10] x, y
+  // of one call (grow-only)
+  char *split_buf[kStreams] = {};
+  int64_t split_cap = 0;
+  int32_t *h_idx = nullptr, *d_idx = nullptr;  // mapped: d_* is the device's view
+  double *h_head = nullptr, *d_head = nullptr;
+  int64_t h_cap = 0;
+  void release_split() {
+    for (int i = 0; i < kStreams; i++) {
+      if (split_buf[i]) cudaFree(split_buf[i]);
+      split_buf[i] = nullptr;
+    }
+    split_cap = 0;
+  }
   void release() {
+    release_split();
     for (int i = 0; i < kStreams; i++) {
       if (in_buf[i]) cudaFree(in_buf[i]);
       if (out_buf[i]) cudaFree(out_buf[i]);
@@ -352,7 +379,11 @@ struct Staging {
     }
     cap = 0;
   }
-  ~Staging() { release(); }
+  ~Staging() {
+    release();
+    if (h_idx) cudaFreeHost(h_idx);
+    if (h_head) cudaFreeHost(h_head);
+  }
 };
 
 thread_local Staging t_stage;
@@ -369,11 +400,93 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
     }                                                               \
   } while (0)
 
-}  // namespace
+constexpr int kTailLen = PP_PATH_LEN - PP_PREV_KEEP;
 
-extern "C" int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const pp_frames *in,
-                                  const pp_plans *out, int64_t n_frames) {
+// Split rows, step 1: columns PP_PREV_KEEP.. of the trajectory rows -> compact [n][kTailLen]
+// rows (a flat run for the download; a pitched copy of 320-byte rows is a poor DMA shape, see
+// below).  One double2 per thread and trip, x and y in the same pass.
+__global__ void __launch_bounds__(256)
+k_split_tail(const double *__restrict__ nx, const double *__restrict__ ny, int64_t n,
+             double *__restrict__ tx, double *__restrict__ ty) {
+  constexpr int kPairs = kTailLen / 2;
+  const int64_t total = n * kPairs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / kPairs;
+    const int col = (int)(i - row * kPairs);
+    const int64_t src = row * (PP_PATH_LEN / 2) + PP_PREV_KEEP / 2 + col;
+    reinterpret_cast<double2 *>(tx)[i] = reinterpret_cast<const double2 *>(nx)[src];
+    reinterpret_cast<double2 *>(ty)[i] = reinterpret_cast<const double2 *>(ny)[src];
+  }
+}
+static_assert(PP_PATH_LEN % 2 == 0 && PP_PREV_KEEP % 2 == 0, "k_split_tail copies double2");
+
+// Split rows, step 2: the first PP_PREV_KEEP points of the listed frames (those that kept no
+// previous points: all 50 of theirs are new) -> compact [k][PP_PREV_KEEP] rows.
+__global__ void __launch_bounds__(256)
+k_gather_heads(const double *__restrict__ nx, const double *__restrict__ ny,
+               const int32_t *__restrict__ idx, int64_t k, double *__restrict__ hx,
+               double *__restrict__ hy) {
+  const int64_t total = k * PP_PREV_KEEP;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i / PP_PREV_KEEP;
+    const int col = (int)(i - j * PP_PREV_KEEP);
+    const int64_t src = (int64_t)idx[j] * PP_PATH_LEN + col;
+    hx[i] = nx[src];
+    hy[i] = ny[src];
+  }
+}
+
+// The per-frame scalars (44 of the 636 input bytes, 20 of the 660 output bytes of a frame) do
+// not go through the copy engines when the caller's arrays are page-locked: twelve copies of
+// 0.5-1 MB per chunk cost the duplex pipeline more than their bytes (profiles/
+// r2_pcie_small.log: 17.1 ms per 1M frames with them, 16.0 without, 16.7 with this kernel).
+// One launch per chunk and direction moves them between the host arrays, read or written in
+// place over PCIe, and the staging buffers.
+constexpr int kMoveMax = 18;
+struct Move {
+  const char *src[kMoveMax];
+  char *dst[kMoveMax];
+  int bytes[kMoveMax];  // 4 or 8 per element
+  int count;
+};
+constexpr int kMoveBlocks = 64;  // blocks: 16 is too few (18.7 ms), 64 and 296 alike
+
+__global__ void __launch_bounds__(256) k_move_small(const Move p, int64_t n) {
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int f = 0; f < p.count; f++) {
+    if (p.bytes[f] == 8) {
+      const double *s = reinterpret_cast<const double *>(p.src[f]);
+      double *d = reinterpret_cast<double *>(p.dst[f]);
+      for (int64_t i = i0; i < n; i += step) d[i] = s[i];
+    } else {
+      const int32_t *s = reinterpret_cast<const int32_t *>(p.src[f]);
+      int32_t *d = reinterpret_cast<int32_t *>(p.dst[f]);
+      for (int64_t i = i0; i < n; i += step) d[i] = s[i];
+    }
+  }
+}
+
+// the device's view of a page-locked host pointer, or null when the memory is pageable
+char *mapped_view(const void *host) {
+  if (!host) return nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return a.type == cudaMemoryTypeHost ? (char *)a.devicePointer : nullptr;
+}
+
+int plan_host(const pp_map *map, const pp_config *cfg, const pp_frames *in, const pp_plans *out,
+              const pp_split_rows *split, int64_t n_frames) {
   if (!map || !cfg || !in || !out || n_frames < 0) return PP_E_ARG;
+  if (split) {  // the trajectories come back in two parts instead of whole rows
+    if (!split->head_x || !split->head_y || !split->tail_x || !split->tail_y) return PP_E_ARG;
+    if (out->next_x || out->next_y) return PP_E_ARG;
+  }
   if (!map->dev_table) {
     ppi::set_cuda_error("pp_plan_batch_host: map has no device table (no usable CUDA device)", 0,
                         "");
@@ -414,7 +527,7 @@ extern "C" int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const
   if (mc > 0)
     for (int i = 9; i < 14; i++)
       if (!hin[i].p) return PP_E_ARG;
-  for (int i = 0; i < 7; i++)
+  for (int i = split ? 2 : 0; i < 7; i++)
     if (!hout[i].p) return PP_E_ARG;
 
   int dev = 0;
@@ -439,6 +552,25 @@ extern "C" int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const
     sg.in_bytes = in_bpf;
     sg.out_bytes = out_bpf;
   }
+  // split rows: which frames kept no previous points is known from the caller's prev_n (the
+  // rule of ego_state, src/main.cpp:1261), so the lists are built here, on the host
+  int64_t n_short = 0;
+  if (split) {
+    if (sg.split_cap < sg.cap) {
+      sg.release_split();
+      const size_t c = (size_t)sg.cap;
+      const size_t bytes = 2 * align256(c * kTailLen * 8);
+      for (int i = 0; i < kStreams; i++) CK(cudaMalloc(&sg.split_buf[i], bytes));
+      sg.split_cap = sg.cap;
+    }
+  }
+  // the scalars that can bypass the copy engines (PP_HOST_NO_ZERO_COPY: never)
+  static const bool zero_copy = getenv("PP_HOST_NO_ZERO_COPY") == nullptr;
+  char *min_view[kIn] = {}, *mout_view[23] = {};
+  if (zero_copy) {
+    for (int i : {0, 1, 2, 3, 4, 7, 8}) min_view[i] = mapped_view(hin[i].p);
+    for (int i = 2; i < 17; i++) mout_view[i] = mapped_view(hout[i].p);
+  }
 
   // (Measured and dropped, profiles/bench_r2b_n1_{pitched,flat}_d2h.json: bringing down only the
   // 40 new columns of a trajectory with a pitched copy — the 10 kept ones are the caller's own
@@ -454,8 +586,18 @@ extern "C" int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const
       cudaGetLastError();
     }
   } join_on_exit{sg};
+  // experiments only (profiles/r2_e2e_parts.log): leave out the uploads (1), the kernels (2)
+  // or the downloads (4) to see what each part of the pipeline costs
+  static const int64_t probe = env_i64("PP_HOST_PROBE", 0);
   int slot = 0;
   int64_t lo = 0;
+  int64_t short_done = 0;  // entries of h_idx / h_head used by the chunks so far
+  std::vector<int64_t> short_of(sizes.size(), 0);
+  int sms = 148;
+  if (split && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError();
+    sms = 148;
+  }
   for (size_t ci = 0; ci < sizes.size(); lo += sizes[ci], ci++, slot = (slot + 1) % kStreams) {
     const int64_t cnt = sizes[ci];
     cudaStream_t st = sg.streams[slot];
@@ -469,13 +611,45 @@ extern "C" int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const
     }
     off = 0;
     for (int i = 0; i < 23; i++) {
-      dout[i] = hout[i].p ? (void *)(sg.out_buf[slot] + off) : nullptr;
+      dout[i] = (hout[i].p || i < 2) ? (void *)(sg.out_buf[slot] + off) : nullptr;
       off += align256(hout[i].bpf * (size_t)sg.cap);
     }
+    Move mv;
+    mv.count = 0;
     for (int i = 0; i < kIn; i++) {
-      if (!hin[i].p || hin[i].bpf == 0) continue;
+      if (!hin[i].p || hin[i].bpf == 0 || (probe & 1)) continue;
+      if (min_view[i]) {
+        mv.src[mv.count] = min_view[i] + hin[i].bpf * (size_t)lo;
+        mv.dst[mv.count] = (char *)din[i];
+        mv.bytes[mv.count++] = (int)hin[i].bpf;
+        continue;
+      }
       CK(cudaMemcpyAsync((void *)din[i], (const char *)hin[i].p + hin[i].bpf * (size_t)lo,
                          hin[i].bpf * (size_t)cnt, cudaMemcpyHostToDevice, st));
+    }
+    if (mv.count) {
+      k_move_small<<<kMoveBlocks, 256, 0, st>>>(mv, cnt);
+      ppi::count_launch(1);
+    }
+    if (split && ci == 0) {
+      // How many frames kept nothing, for the size of the pinned lists: counted while the first
+      // chunk's upload is under way.
+      for (int64_t f = 0; f < n_frames; f++) n_short += in->prev_n[f] < PP_PREV_KEEP;
+      if (n_short > sg.h_cap) {
+        if (sg.h_idx) cudaFreeHost(sg.h_idx);
+        if (sg.h_head) cudaFreeHost(sg.h_head);
+        sg.h_idx = nullptr;
+        sg.h_head = nullptr;
+        sg.h_cap = 0;
+        sg.d_idx = nullptr;
+        sg.d_head = nullptr;
+        CK(cudaHostAlloc((void **)&sg.h_idx, (size_t)n_short * 4, cudaHostAllocMapped));
+        CK(cudaHostAlloc((void **)&sg.h_head, (size_t)n_short * 2 * PP_PREV_KEEP * 8,
+                         cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer((void **)&sg.d_idx, sg.h_idx, 0));
+        CK(cudaHostGetDevicePointer((void **)&sg.d_head, sg.h_head, 0));
+        sg.h_cap = n_short;
+      }
     }
     pp_frames fin;
     fin.ego_x = (const double *)din[0];
@@ -523,14 +697,82 @@ extern "C" int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const
     fout.car_vd = (double *)dout[20];
     fout.car_lane = (int32_t *)dout[21];
     fout.car_next_wp = (int32_t *)dout[22];
-    int rc = pp_plan_batch(map, cfg, &fin, &fout, cnt, st);
+    int rc = (probe & 2) ? PP_OK : pp_plan_batch(map, cfg, &fin, &fout, cnt, st);
     if (rc != PP_OK) return rc;
+    if (probe & 4) continue;
+    if (split) {
+      const size_t c = (size_t)sg.split_cap;
+      char *sb = sg.split_buf[slot];
+      double *d_tx = (double *)sb;
+      double *d_ty = (double *)(sb + align256(c * kTailLen * 8));
+      k_split_tail<<<sms * 8, 256, 0, st>>>(fout.next_x, fout.next_y, cnt, d_tx, d_ty);
+      ppi::count_launch(1);
+      CK(cudaMemcpyAsync(split->tail_x + (size_t)lo * kTailLen, d_tx, (size_t)cnt * kTailLen * 8,
+                         cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(split->tail_y + (size_t)lo * kTailLen, d_ty, (size_t)cnt * kTailLen * 8,
+                         cudaMemcpyDeviceToHost, st));
+      // this chunk's frames without kept points: the kernel reads the (chunk-local) index list
+      // from the pinned host block and writes the heads into it, in place over PCIe
+      int64_t k = 0;
+      int32_t *list = sg.h_idx + short_done;
+      for (int64_t f = 0; f < cnt; f++)
+        if (in->prev_n[lo + f] < PP_PREV_KEEP) list[k++] = (int32_t)f;
+      if (k > 0) {
+        double *hh = sg.d_head + (size_t)short_done * 2 * PP_PREV_KEEP;
+        const int64_t want = (k * PP_PREV_KEEP + 255) / 256;
+        k_gather_heads<<<(int)(want < kMoveBlocks ? want : kMoveBlocks), 256, 0, st>>>(
+            fout.next_x, fout.next_y, sg.d_idx + short_done, k, hh, hh + (size_t)k * PP_PREV_KEEP);
+        ppi::count_launch(1);
+        short_done += k;
+        short_of[ci] = k;
+      }
+    }
+    mv.count = 0;
     for (int i = 0; i < 23; i++) {
       if (!hout[i].p || hout[i].bpf == 0) continue;
+      if (mout_view[i]) {
+        mv.src[mv.count] = (const char *)dout[i];
+        mv.dst[mv.count] = mout_view[i] + hout[i].bpf * (size_t)lo;
+        mv.bytes[mv.count++] = (int)hout[i].bpf;
+        continue;
+      }
       CK(cudaMemcpyAsync((char *)hout[i].p + hout[i].bpf * (size_t)lo, dout[i],
                          hout[i].bpf * (size_t)cnt, cudaMemcpyDeviceToHost, st));
     }
+    if (mv.count) {
+      k_move_small<<<kMoveBlocks, 256, 0, st>>>(mv, cnt);
+      ppi::count_launch(1);
+    }
   }
   for (int i = 0; i < kStreams; i++) CK(cudaStreamSynchronize(sg.streams[i]));
+  if (split && n_short > 0) {  // the gathered heads into their rows (80 bytes each, few frames)
+    int64_t used = 0, base = 0;
+    for (size_t ci = 0; ci < sizes.size(); base += sizes[ci], ci++) {
+      const int64_t k = short_of[ci];
+      const int32_t *list = sg.h_idx + used;
+      const double *hx = sg.h_head + (size_t)used * 2 * PP_PREV_KEEP;
+      const double *hy = hx + (size_t)k * PP_PREV_KEEP;
+      for (int64_t j = 0; j < k; j++) {
+        const size_t row = (size_t)(base + list[j]) * PP_PREV_KEEP;
+        std::memcpy(split->head_x + row, hx + (size_t)j * PP_PREV_KEEP, PP_PREV_KEEP * 8);
+        std::memcpy(split->head_y + row, hy + (size_t)j * PP_PREV_KEEP, PP_PREV_KEEP * 8);
+      }
+      used += k;
+    }
+  }
   return PP_OK;
+}
+
+}  // namespace
+
+extern "C" int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const pp_frames *in,
+                                  const pp_plans *out, int64_t n_frames) {
+  return plan_host(map, cfg, in, out, nullptr, n_frames);
+}
+
+extern "C" int pp_plan_batch_host_split(const pp_map *map, const pp_config *cfg,
+                                        const pp_frames *in, const pp_plans *out,
+                                        const pp_split_rows *rows, int64_t n_frames) {
+  if (!rows) return PP_E_ARG;
+  return plan_host(map, cfg, in, out, rows, n_frames);
 }

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PP_VERSION 101
+#define PP_VERSION 102
 
 /* Fixed sizes of the reference's planning step. */
 #define PP_NUM_LANES 3    /* src/main.cpp:22  NUM_LANES */
@@ -210,6 +210,26 @@ int pp_plan_batch(const pp_map *map, const pp_config *cfg, const pp_frames *in,
  * buffers are complete.  This is the drop-in for a CPU caller. */
 int pp_plan_batch_host(const pp_map *map, const pp_config *cfg, const pp_frames *in,
                        const pp_plans *out, int64_t n_frames);
+
+/* The same call for a caller that does not want its own points sent back over PCIe.  A frame
+ * with prev_n >= PP_PREV_KEEP keeps its first PP_PREV_KEEP previous points as the first points
+ * of the new trajectory, verbatim (result_points = prev_trajectory, src/main.cpp:578,
+ * 1446-1452) — the caller already holds them in in->prev_x / in->prev_y.  Here a trajectory
+ * comes back in two parts, and out->next_x / out->next_y must be NULL:
+ *   tail_x, tail_y [n][PP_PATH_LEN - PP_PREV_KEEP]  points PP_PREV_KEEP.. of every frame;
+ *   head_x, head_y [n][PP_PREV_KEEP]                points 0..PP_PREV_KEEP-1.  The library writes
+ *       a head row ONLY for a frame that kept nothing (prev_n < PP_PREV_KEEP: all its points are
+ *       new); every other row is left as the caller has it.  head_x / head_y may be the very
+ *       buffers passed as in->prev_x / in->prev_y (they are read before they are written), and
+ *       then hold the first points of every trajectory on return.
+ * head ++ tail of frame i equals row i of pp_plan_batch_host's next_x / next_y bit for bit
+ * (tests/test_gpu_parity.py); 160 of the 820 bytes per frame stay off the bus. */
+typedef struct pp_split_rows {
+  double *head_x, *head_y;
+  double *tail_x, *tail_y;
+} pp_split_rows;
+int pp_plan_batch_host_split(const pp_map *map, const pp_config *cfg, const pp_frames *in,
+                             const pp_plans *out, const pp_split_rows *rows, int64_t n_frames);
 
 /* Aggregate statistics of a planned batch on the device:
  * stats_dev[PP_STATS_LEN] (int64, overwritten).  The multi-GPU job all-reduces
@@ -409,6 +429,11 @@ int pp_speed_controller_batch(int32_t op, const double *start, double *target, d
  * cudaMemcpy (synchronous) / cudaDeviceSynchronize on the current device. */
 int pp_dev_alloc(void **out, size_t bytes);
 int pp_dev_free(void *p);
+/* Page-locked host memory (cudaHostAlloc / cudaFreeHost): what the buffers handed to
+ * pp_plan_batch_host[_split] should live in — copies from pageable memory are staged by the
+ * driver and do not overlap with anything. */
+int pp_host_alloc(void **out, size_t bytes);
+int pp_host_free(void *p);
 int pp_dev_upload(void *dst_dev, const void *src_host, size_t bytes);
 int pp_dev_download(void *dst_host, const void *src_dev, size_t bytes);
 int pp_dev_sync(void);

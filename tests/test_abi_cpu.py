@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(pp):
     for n in names:
         assert hasattr(pp.lib, n), f"libpp_b200.so does not export {n}"
     assert sorted(pp.EXPORTS) == names
-    assert pp.lib.pp_version() == 101
+    assert pp.lib.pp_version() == 102
 
 
 def test_product_does_not_reference_the_oracle():

@@ -243,6 +243,92 @@ def test_host_entry_point_equals_device_entry_point(pp, torch_cuda, gmap, cold):
         assert np.array_equal(getattr(host, k), getattr(dev, k), equal_nan=True), k
 
 
+@pytest.mark.parametrize("cold", ["none", "few", "some", "most"])
+def test_split_rows_host_entry_point(pp, torch_cuda, gmap, cold):
+    """pp_plan_batch_host_split: head ++ tail == the whole rows of pp_plan_batch_host, bit for
+    bit; head rows of frames that kept their previous points are not touched, so passing the
+    frames' own prev_x / prev_y as the heads leaves the first points of every trajectory there
+    (result_points = prev_trajectory, src/main.cpp:578)."""
+    n = 150000
+    fb = pp.synth_frames(gmap, n, 12, seed=43, rare_permille=0 if cold == "none" else 20)
+    rng = np.random.default_rng(43)
+    if cold == "some":
+        fb.prev_n[rng.random(n) < 0.1] = 3
+    elif cold == "most":
+        fb.prev_n[rng.random(n) < 0.6] = 0
+        fb.prev_n[:40000] = 47
+    elif cold == "none":
+        fb.prev_n[:] = np.maximum(fb.prev_n, pp.PREV_KEEP)
+    whole = pp.plan_batch_host(gmap, fb, diag=False, cars=False)
+    keep, tail_len = pp.PREV_KEEP, pp.PATH_LEN - pp.PREV_KEEP
+    sp = pp.PlanBatch(n, fb.max_cars, diag=False, cars=False)
+    sp.next_x = sp.next_y = None
+    sp.fields = [f for f in sp.fields if f not in ("next_x", "next_y")]
+    sentinel = -12345.0
+    head_x = np.full((n, keep), sentinel)
+    head_y = np.full((n, keep), sentinel)
+    tail_x = np.full((n, tail_len), sentinel)
+    tail_y = np.full((n, tail_len), sentinel)
+    pp.plan_batch_host_split(gmap, fb, sp, head_x, head_y, tail_x, tail_y)
+    for k in sp.fields:
+        assert np.array_equal(getattr(sp, k), getattr(whole, k)), k
+    kept = fb.prev_n >= keep
+    assert np.array_equal(tail_x, whole.next_x[:, keep:], equal_nan=True)
+    assert np.array_equal(tail_y, whole.next_y[:, keep:], equal_nan=True)
+    assert np.all(head_x[kept] == sentinel) and np.all(head_y[kept] == sentinel)  # not touched
+    assert np.array_equal(head_x[~kept], whole.next_x[~kept, :keep], equal_nan=True)
+    assert np.array_equal(head_y[~kept], whole.next_y[~kept, :keep], equal_nan=True)
+    # the kept points ARE the caller's previous points
+    full = whole.n_points == pp.PATH_LEN
+    assert np.array_equal(whole.next_x[kept & full, :keep], fb.prev_x[kept & full], equal_nan=True)
+    assert np.array_equal(whole.next_y[kept & full, :keep], fb.prev_y[kept & full], equal_nan=True)
+    # heads aliased onto the inputs: on return they hold the first points of every trajectory
+    fb2 = fb.slice(0, n)
+    fb2.prev_x, fb2.prev_y = fb.prev_x.copy(), fb.prev_y.copy()
+    pp.plan_batch_host_split(gmap, fb2, sp, fb2.prev_x, fb2.prev_y, tail_x, tail_y)
+    assert np.array_equal(fb2.prev_x[full], whole.next_x[full, :keep], equal_nan=True)
+    assert np.array_equal(fb2.prev_y[full], whole.next_y[full, :keep], equal_nan=True)
+    assert np.array_equal(tail_x, whole.next_x[:, keep:], equal_nan=True)
+    # whole rows asked for as well: refused
+    bad = pp.PlanBatch(8, fb.max_cars, diag=False, cars=False)
+    with pytest.raises(pp.PPError):
+        pp.plan_batch_host_split(gmap, fb.slice(0, 8), bad, head_x, head_y, tail_x, tail_y)
+
+
+def test_host_entry_points_with_page_locked_buffers(pp, torch_cuda, gmap):
+    """Page-locked caller buffers (pp_host_alloc): the per-frame scalars are then read and
+    written in place by a kernel instead of the copy engines.  Same bytes as with pageable
+    buffers, diagnostics and per-car outputs included."""
+    n = 140001
+    fb = pp.synth_frames(gmap, n, 12, seed=47)
+    fb.prev_n[::7] = 2
+    want = pp.plan_batch_host(gmap, fb)  # pageable numpy arrays: copies only
+    pf = pp.FrameBatch(n, fb.max_cars)
+    for k, v in fb.arrays().items():
+        setattr(pf, k, pp.pinned_like(v))
+    got = pp.PlanBatch(n, fb.max_cars)
+    for k in got.fields:
+        setattr(got, k, pp.pinned_like(getattr(got, k)))
+    pp.plan_batch_host(gmap, pf, got)
+    for k in got.fields:
+        assert np.array_equal(getattr(got, k), getattr(want, k), equal_nan=True), k
+    keep = pp.PREV_KEEP
+    sp = pp.PlanBatch(n, fb.max_cars, cars=False)
+    sp.fields = [f for f in sp.fields if f not in ("next_x", "next_y")]
+    sp.next_x = sp.next_y = None
+    for k in sp.fields:
+        setattr(sp, k, pp.pinned_like(getattr(sp, k)))
+    tx, ty = pp.pinned_empty((n, pp.PATH_LEN - keep)), pp.pinned_empty((n, pp.PATH_LEN - keep))
+    pp.plan_batch_host_split(gmap, pf, sp, pf.prev_x, pf.prev_y, tx, ty)
+    for k in sp.fields:
+        assert np.array_equal(getattr(sp, k), getattr(want, k), equal_nan=True), k
+    full = want.n_points == pp.PATH_LEN
+    assert np.array_equal(tx, want.next_x[:, keep:], equal_nan=True)
+    assert np.array_equal(ty, want.next_y[:, keep:], equal_nan=True)
+    assert np.array_equal(pf.prev_x[full], want.next_x[full, :keep], equal_nan=True)
+    assert np.array_equal(pf.prev_y[full], want.next_y[full, :keep], equal_nan=True)
+
+
 def test_properties_at_full_size(pp, torch_cuda, gmap, oracle):
     """BASELINE config 2 size (1,048,576 frames, 12 cars): properties that do
     not need the CPU to plan a million frames, plus a 1/64 sample that does."""
