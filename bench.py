@@ -184,7 +184,9 @@ def run_rollouts(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    # (a job of thousands of short launches: NVML polled every 2 ms from another thread costs it
+    # 2 % and its steadiness, profiles/r2_rollouts_sampler.log; every 20 ms it does not)
+    sampler = ClockSampler(local, period_s=0.02) if rank == 0 else None
     launches0 = pp.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     steps = max(1, args.steps if args.steps != 50 else 1)
@@ -287,8 +289,9 @@ class ClockSampler:
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap"}
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.002):
         import threading
+        self.period_s = float(os.environ.get("PP_BENCH_CLOCK_MS", period_s * 1e3)) * 1e-3
         self.samples, self.maxes, self.reasons = [], [], set()
         self.stop_flag = False
         self.ok = False
@@ -333,7 +336,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period_s)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}

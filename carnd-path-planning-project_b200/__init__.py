@@ -44,7 +44,7 @@ EXPORTS = [
     "pp_dev_alloc", "pp_dev_free", "pp_host_alloc", "pp_host_free", "pp_dev_upload", "pp_dev_download", "pp_dev_sync",
     "pp_dev_set", "pp_stream_create", "pp_stream_sync", "pp_stream_destroy",
     "pp_rollouts_create", "pp_rollouts_destroy", "pp_rollouts_run", "pp_rollouts_last",
-    "pp_rollouts_get_state", "pp_rollouts_stats", "pp_rollouts_set_lean", "pp_sweep_batch",
+    "pp_rollouts_get_state", "pp_rollouts_stats", "pp_rollouts_set_lean", "pp_rollouts_set_groups", "pp_sweep_batch",
     "pp_set_pipes", "pp_plan_stats_batch", "pp_synth_frames_dev", "pp_fstats_batch",
     "pp_comm_unique_id", "pp_comm_init_rank", "pp_comm_init_all", "pp_comm_destroy",
     "pp_comm_group_begin", "pp_comm_group_end", "pp_stats_reduce",
@@ -428,6 +428,10 @@ class Rollouts:
                                       C.c_int64(first), C.byref(self._h)), "pp_rollouts_create")
         if lean:
             _check(lib.pp_rollouts_set_lean(self._h, C.c_int(1)), "pp_rollouts_set_lean")
+
+    def set_groups(self, groups: int):
+        """Stream groups per tick (0 = automatic)."""
+        _check(lib.pp_rollouts_set_groups(self._h, C.c_int(groups)), "pp_rollouts_set_groups")
 
     def run(self, ticks: int, consume_k: int = 1, cfg: Config | None = None, stream=None):
         import torch

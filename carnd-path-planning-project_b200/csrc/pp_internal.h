@@ -38,9 +38,14 @@ int check_map_device(const pp_map *map, const char *who);
 
 // pp_plan.cu: the pipeline with caller-owned scratch (see there)
 size_t plan_scratch_bytes(int64_t n_frames, int max_cars);
+// xsum_add (used when stats_dev is null): the pipeline's kernels ADD the checksum of the
+// trajectories they write (PP_STAT_XSUM) to *xsum_add, nothing is cleared; honoured only when
+// plan_adds_checksum(n_frames) — the single-kernel paths of small batches do not take it.
 int plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_frames *in,
                        const pp_plans *out, int64_t n_frames, void *cuda_stream,
-                       char *caller_scratch, int64_t *stats_dev);
+                       char *caller_scratch, int64_t *stats_dev,
+                       unsigned long long *xsum_add = nullptr);
+bool plan_adds_checksum(int64_t n_frames);
 
 // pp_frames / pp_plans advanced by `lo` frames
 inline pp_frames offset_frames(const pp_frames &a, int64_t lo) {

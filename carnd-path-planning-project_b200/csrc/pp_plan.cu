@@ -1905,9 +1905,15 @@ extern "C" int pp_plan_stats_batch(const pp_map *map, const pp_config *cfg, cons
 // pp_plan_batch with the scratch supplied by the caller (plan_scratch_bytes; nullptr: taken
 // from the stream-ordered pool).  The rollout engine owns its scratch so that a tick is pure
 // kernel / memset / event work and can be replayed as a CUDA graph.
+bool ppi::plan_adds_checksum(int64_t n_frames) {
+  const int variant = g_variant.load(std::memory_order_relaxed);
+  return !(variant == 1 || variant == 4 || (variant == 0 && n_frames < kFusedBelow));
+}
+
 int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_frames *in,
                             const pp_plans *out, int64_t n_frames, void *cuda_stream,
-                            char *caller_scratch, int64_t *stats_dev) {
+                            char *caller_scratch, int64_t *stats_dev,
+                            unsigned long long *xsum_add) {
   if (!map || !cfg || !in || !out || n_frames < 0) return PP_E_ARG;
   int rc0;
   if (stats_dev &&
@@ -2063,7 +2069,7 @@ int ppi::plan_batch_scratch(const pp_map *map, const pp_config *cfg, const pp_fr
     sc.slow_na = n_base + 2 * ci;
     sc.slow_nb = n_base + 2 * ci + 1;
     sc.dbg = dbg ? n_base + 2 * n_chunks : nullptr;
-    sc.xsum = stats_dev ? (unsigned long long *)stats_dev + PP_STAT_XSUM : nullptr;
+    sc.xsum = stats_dev ? (unsigned long long *)stats_dev + PP_STAT_XSUM : xsum_add;
     // how the kept points leave k_decide_t (see there); the tensor maps describe THIS chunk's rows
     CUtensorMap tm_x, tm_y;
     std::memset(&tm_x, 0, sizeof tm_x);

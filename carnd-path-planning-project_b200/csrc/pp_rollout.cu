@@ -45,11 +45,12 @@ struct pp_rollouts {
   int32_t graph_k = 0;
   pp_config graph_cfg;
   int64_t launches_per_tick = 0;
+  int groups_wanted = 0;  // pp_rollouts_set_groups: 0 = automatic
 };
 
 namespace {
 
-constexpr int kB = 128;
+constexpr int kB = 256;
 constexpr double kTick = 0.02;
 
 // splitmix64, as in pp_synth.cpp
@@ -129,32 +130,47 @@ struct SimState {
   int64_t *ticks;
 };
 
-// frame <- state.  A block owns kB consecutive rollouts: one thread per rollout writes the ego
-// part, then the block's threads sweep the rollouts' car slots (coalesced).
+// Both simulator kernels give a block of kB threads only kR rollouts: at 8,192 rollouts per stream
+// group a tick is a chain of short dependent kernels, the job is bound by how long ONE frame
+// takes to get through that chain (frames in flight / latency), and with a rollout per thread
+// these two kernels were 31 and 68 us of it — twelve dependent trips over a thread's car slots,
+// fifty over its trajectory row.  Eight threads per rollout make that two trips and seven.
+constexpr int kR = 32;  // rollouts per block (one warp's worth: the ego part is one warp)
+
+// frame <- state.  The block's threads sweep the rollouts' scalars (a warp per field), their
+// kept points and their car slots, all coalesced.
 __global__ void __launch_bounds__(kB)
 k_sim_frames(Track trk, int64_t lo, int64_t n, int c, SimState st, pp_plans pl, pp_frames fr) {
-  const int64_t r0 = lo + (int64_t)blockIdx.x * blockDim.x;
-  const int64_t r = r0 + threadIdx.x;
-  if (r < lo + n) {
-    const_cast<double *>(fr.ego_x)[r] = st.ego_x[r];
-    const_cast<double *>(fr.ego_y)[r] = st.ego_y[r];
-    const_cast<double *>(fr.ego_yaw_deg)[r] = st.ego_yaw[r];
-    const_cast<double *>(fr.ego_speed_mph)[r] = st.ego_mph[r];
-    const int pn = st.path_n[r];
-    const_cast<int32_t *>(fr.prev_n)[r] = pn;
-    const double *nx = pl.next_x + r * PP_PATH_LEN + st.path_off[r];
-    const double *ny = pl.next_y + r * PP_PATH_LEN + st.path_off[r];
-    for (int i = 0; i < PP_PREV_KEEP; i++) {
-      const bool have = i < pn;
-      const_cast<double *>(fr.prev_x)[r * PP_PREV_KEEP + i] = have ? nx[i] : 0.0;
-      const_cast<double *>(fr.prev_y)[r * PP_PREV_KEEP + i] = have ? ny[i] : 0.0;
-    }
-    const_cast<int32_t *>(fr.target_lane_in)[r] = st.target_lane[r];
-    const_cast<int32_t *>(fr.n_cars)[r] = c;
-  }
-  int64_t r_end = r0 + blockDim.x;
+  const int64_t r0 = lo + (int64_t)blockIdx.x * kR;
+  int64_t r_end = r0 + kR;
   if (r_end > lo + n) r_end = lo + n;
-  for (int64_t q = r0 * c + threadIdx.x; q < r_end * c; q += blockDim.x) {
+  const int nr = (int)(r_end - r0);
+  {  // ego scalars: warp w copies field w
+    const int field = threadIdx.x >> 5, rr = threadIdx.x & 31;
+    const int64_t r = r0 + rr;
+    if (rr < nr) {
+      switch (field) {
+        case 0: const_cast<double *>(fr.ego_x)[r] = st.ego_x[r]; break;
+        case 1: const_cast<double *>(fr.ego_y)[r] = st.ego_y[r]; break;
+        case 2: const_cast<double *>(fr.ego_yaw_deg)[r] = st.ego_yaw[r]; break;
+        case 3: const_cast<double *>(fr.ego_speed_mph)[r] = st.ego_mph[r]; break;
+        case 4: const_cast<int32_t *>(fr.prev_n)[r] = st.path_n[r]; break;
+        case 5: const_cast<int32_t *>(fr.target_lane_in)[r] = st.target_lane[r]; break;
+        case 6: const_cast<int32_t *>(fr.n_cars)[r] = c; break;
+        default: break;
+      }
+    }
+  }
+  // kept points: the unconsumed points of the last plan, behind path_off
+  for (int e = threadIdx.x; e < nr * PP_PREV_KEEP; e += kB) {
+    const int rr = e / PP_PREV_KEEP, i = e - rr * PP_PREV_KEEP;
+    const int64_t r = r0 + rr;
+    const bool have = i < st.path_n[r];
+    const int64_t src = r * PP_PATH_LEN + st.path_off[r] + i;
+    const_cast<double *>(fr.prev_x)[r0 * PP_PREV_KEEP + e] = have ? pl.next_x[src] : 0.0;
+    const_cast<double *>(fr.prev_y)[r0 * PP_PREV_KEEP + e] = have ? pl.next_y[src] : 0.0;
+  }
+  for (int64_t q = r0 * c + threadIdx.x; q < r_end * c; q += kB) {
     double x, y, vx, vy;
     trk.car(st.car_lane[q], st.car_wp[q], st.car_ratio[q], st.car_speed[q], x, y, vx, vy);
     const_cast<int32_t *>(fr.car_id)[q] = (int32_t)(q % c);
@@ -164,21 +180,25 @@ k_sim_frames(Track trk, int64_t lo, int64_t n, int c, SimState st, pp_plans pl, 
     const_cast<double *>(fr.car_vy)[q] = vy;
   }
 }
+static_assert(kB >= 7 * 32 && kR == 32, "k_sim_frames: a warp per scalar field, a lane per rollout");
 
 // state <- simulator step(plan), and this tick's contribution to the aggregate statistics
-// (definition: pp_stats_batch).  Same block layout: the car slots first (they read the rollout's
-// tick before it is counted), then one thread per rollout for the ego; the trajectory checksum
-// is taken by the warp over its 32 rollouts' rows with coalesced loads.
+// (definition: pp_stats_batch).  The car slots first (they read the rollout's tick before it is
+// counted), then one warp for the egos.  The trajectory checksum normally comes from the planning
+// kernels, which add it up as they write the points (plan_batch_scratch, xsum_add): re-reading
+// 800 bytes per rollout for it was two thirds of this kernel's traffic.  For the single-kernel
+// paths of small jobs the block takes it here, over its rollouts' rows (one contiguous run).
 __global__ void __launch_bounds__(kB)
 k_sim_advance(Track trk, int64_t lo, int64_t n, int c, uint64_t seed, int64_t first, int consume_k,
-              SimState st, pp_plans pl, unsigned long long *stats_sum) {
+              SimState st, pp_plans pl, unsigned long long *stats_sum, int do_xsum) {
   __shared__ unsigned long long s_acc[PP_STATS_LEN];
   for (int i = threadIdx.x; i < PP_STATS_LEN; i += blockDim.x) s_acc[i] = 0;
-  const int64_t r0 = lo + (int64_t)blockIdx.x * blockDim.x;
-  int64_t r_end = r0 + blockDim.x;
+  const int64_t r0 = lo + (int64_t)blockIdx.x * kR;
+  int64_t r_end = r0 + kR;
   if (r_end > lo + n) r_end = lo + n;
+  const int nr = (int)(r_end - r0);
   // ---- traffic (one thread per car slot)
-  for (int64_t q = r0 * c + threadIdx.x; q < r_end * c; q += blockDim.x) {
+  for (int64_t q = r0 * c + threadIdx.x; q < r_end * c; q += kB) {
     const int64_t r = q / c;
     const int j = (int)(q - r * c);
     const int np = pl.n_points[r];
@@ -213,13 +233,26 @@ k_sim_advance(Track trk, int64_t lo, int64_t n, int c, uint64_t seed, int64_t fi
     st.car_ratio[q] = u;
     st.car_speed[q] = v;
   }
+  if (do_xsum) {  // ---- checksum of the block's rows, unless the planning kernels added it
+    long long xs = 0;
+    const int64_t base = r0 * PP_PATH_LEN;
+    for (int e = threadIdx.x; e < nr * PP_PATH_LEN; e += kB) {
+      const int rr = e / PP_PATH_LEN;
+      const int np_r = pl.n_points[r0 + rr];
+      const double x = pl.next_x[base + e], y = pl.next_y[base + e];
+      if (e - rr * PP_PATH_LEN < np_r && x == x && y == y && fabs(x) < 1e12 && fabs(y) < 1e12)
+        xs += (long long)(x * 256.0) + (long long)(y * 256.0);
+    }
+    unsigned long long v = (unsigned long long)xs;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_acc[PP_STAT_XSUM], v);
+  }
   __syncthreads();
-  // ---- the ego consumes k points of the new trajectory (one thread per rollout)
-  const int64_t r = r0 + threadIdx.x;
-  const bool live = r < lo + n;
-  int np = 0;
-  if (live) {
-    np = pl.n_points[r];
+  // ---- the ego consumes k points of the new trajectory (one lane per rollout, one warp)
+  if (threadIdx.x < nr) {
+    const int64_t r = r0 + threadIdx.x;
+    const int np = pl.n_points[r];
     const int k = consume_k < np ? consume_k : np;
     if (k > 0) {
       const double ox = st.ego_x[r], oy = st.ego_y[r];
@@ -242,30 +275,6 @@ k_sim_advance(Track trk, int64_t lo, int64_t n, int c, uint64_t seed, int64_t fi
     if (tl != el) atomicAdd(&s_acc[PP_STAT_LANE_CHANGES], 1ull);
     for (int b = 0; b < PP_NUM_FLAGS; b++)
       if (fl & (1u << b)) atomicAdd(&s_acc[PP_STAT_FLAG0 + b], 1ull);
-  }
-  {  // checksum: the warp walks its 32 rollouts' rows together
-    const int ln = threadIdx.x & 31;
-    const int64_t wr0 = r0 + (threadIdx.x & ~31);
-    long long xs = 0;
-    // the 32 rows are one contiguous run of 1,600 points: 50 coalesced trips, independent of
-    // each other (as a loop over rows every trip waited for the previous row's loads: 64
-    // dependent round trips to memory, a third of this kernel's 68 us)
-    const int64_t base = wr0 * PP_PATH_LEN;
-    const int64_t limit = (lo + n) * PP_PATH_LEN;
-#pragma unroll 10
-    for (int t = 0; t < PP_PATH_LEN; t++) {
-      const int e = t * 32 + ln;
-      const int rr = e / PP_PATH_LEN;
-      const int np_r = __shfl_sync(0xffffffffu, np, rr);
-      const bool in = base + e < limit;
-      const double x = in ? pl.next_x[base + e] : 0.0, y = in ? pl.next_y[base + e] : 0.0;
-      if (in && e - rr * PP_PATH_LEN < np_r && x == x && y == y && fabs(x) < 1e12 && fabs(y) < 1e12)
-        xs += (long long)(x * 256.0) + (long long)(y * 256.0);
-    }
-    unsigned long long v = (unsigned long long)xs;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (ln == 0 && v) atomicAdd(&s_acc[PP_STAT_XSUM], v);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < PP_STATS_LEN; i += blockDim.x)
@@ -487,14 +496,22 @@ int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStre
                bool fork = true, bool join = true) {
   // device rows of the padded table: logical row 0 starts PPD_PAD_ROWS rows in
   const Track trk{r->map->dev_table + (size_t)PPD_PAD_ROWS * PP_MAP_STRIDE, r->map->n, PP_MAP_STRIDE};
-  // groups: contiguous ranges of rollouts (at least 4096 each, so that small jobs stay whole)
-  static const int want_groups = [] {
+  // groups: contiguous ranges of rollouts, at least 16,384 each, at most 8.  A tick of one group
+  // is a chain of eight dependent kernels whose durations simply add up (253 us at 65,536
+  // rollouts under ncu, 254 us per tick measured, profiles/r2_rollouts_chain.csv); with several
+  // groups different kernels of different groups overlap.  65,536 rollouts, four runs each
+  // (profiles/r2_rollouts_groups2.log): 1 group 253-256 M ego-frames/s, 2 groups 271-272 M,
+  // 4 groups 270-283 M, 8 groups 254-263 M (64 launches per tick; the host falls behind); any
+  // of them loses a run now and then to the shared host (79-183 M).
+  // pp_rollouts_set_groups / PP_ROLLOUT_GROUPS override the count (at least 4,096 each then).
+  static const int forced_groups = [] {
     const char *e = getenv("PP_ROLLOUT_GROUPS");
-    const int v = e && *e ? atoi(e) : 8;  // profiles/r2_rollouts.log: 4 groups 78-214 M, 8 groups 217 M every run
-    return v < 1 ? 1 : (v > pp_rollouts::kGroups ? pp_rollouts::kGroups : v);
+    const int v = e && *e ? atoi(e) : 0;
+    return v < 0 ? 0 : (v > pp_rollouts::kGroups ? pp_rollouts::kGroups : v);
   }();
-  int groups = want_groups;
-  while (groups > 1 && r->n / groups < 4096) groups--;
+  const int forced = r->groups_wanted ? r->groups_wanted : forced_groups;
+  int groups = forced ? forced : pp_rollouts::kGroups;
+  while (groups > 1 && r->n / groups < (forced ? 4096 : 16384)) groups--;
   const int64_t per = (r->n + groups - 1) / groups;
   const int mc = r->fr.max_cars;
   if (fork) {
@@ -507,7 +524,7 @@ int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStre
     const int64_t cnt = (r->n - lo) < per ? (r->n - lo) : per;
     if (cnt <= 0) continue;
     cudaStream_t gs = r->gs[g];
-    const int grid = (int)((cnt + kB - 1) / kB);
+    const int grid = (int)((cnt + kR - 1) / kR);
     const pp_frames fr = ppi::offset_frames(r->fr, lo);
     const pp_plans pl = ppi::offset_plans(r->pl, lo, mc);
     const SimState sst{r->ego_x, r->ego_y, r->ego_yaw, r->ego_mph, r->path_n, r->path_off,
@@ -518,10 +535,12 @@ int issue_tick(pp_rollouts *r, const pp_config *cfg, int32_t consume_k, cudaStre
       if (need && cudaMalloc((void **)&r->scratch[g], need) != cudaSuccess)
         return cuda_fail("cudaMalloc(rollout scratch)", cudaGetLastError());
     }
-    int rc = ppi::plan_batch_scratch(r->map, cfg, &fr, &pl, cnt, gs, r->scratch[g], nullptr);
+    const bool plan_sums = ppi::plan_adds_checksum(cnt);
+    int rc = ppi::plan_batch_scratch(r->map, cfg, &fr, &pl, cnt, gs, r->scratch[g], nullptr,
+                                     (unsigned long long *)r->stats_sum + PP_STAT_XSUM);
     if (rc != PP_OK) return rc;
     k_sim_advance<<<grid, kB, 0, gs>>>(trk, lo, cnt, r->c, r->seed, r->first, consume_k, sst, r->pl,
-                                       (unsigned long long *)r->stats_sum);
+                                       (unsigned long long *)r->stats_sum, plan_sums ? 0 : 1);
     ppi::count_launch(2);
   }
   r->launches_per_tick = pp_launch_count() - launches0;
@@ -636,6 +655,16 @@ extern "C" int pp_rollouts_set_lean(pp_rollouts *r, int lean) {
     cudaGraphExecDestroy(r->graph);
     r->graph = nullptr;
   }
+  return PP_OK;
+}
+
+extern "C" int pp_rollouts_set_groups(pp_rollouts *r, int groups) {
+  if (!r || groups < 0 || groups > pp_rollouts::kGroups) return PP_E_ARG;
+  if (r->graph && groups != r->groups_wanted) {  // the captured tick holds the old split
+    cudaGraphExecDestroy(r->graph);
+    r->graph = nullptr;
+  }
+  r->groups_wanted = groups;
   return PP_OK;
 }
 

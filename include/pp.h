@@ -548,6 +548,9 @@ int pp_rollouts_run(pp_rollouts *r, const pp_config *cfg, int64_t n_ticks, int32
  * n_points, lanes, ref_wp, flags, per-car lane and s); the diagnostics and the other per-car
  * outputs are not written (their pointers in pp_rollouts_last are NULL).  Default: everything. */
 int pp_rollouts_set_lean(pp_rollouts *r, int lean);
+/* Stream groups a tick is cut into (1..8, at least 4,096 rollouts each; 0 = automatic: up to 8
+ * groups of at least 16,384 rollouts).  The result does not depend on it. */
+int pp_rollouts_set_groups(pp_rollouts *r, int groups);
 /* Device views of the LAST tick's frames and plans (valid until the next run / destroy). */
 int pp_rollouts_last(const pp_rollouts *r, pp_frames *frames_dev, pp_plans *plans_dev);
 /* Copy the simulator state out (synchronises the device). */

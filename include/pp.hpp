@@ -523,7 +523,10 @@ class Planner {
   pp_config &config() { return cfg_; }
 
   // N frames -> N plans: marshals into the SoA layout of pp_frames and calls
-  // pp_plan_batch_host (upload, the sm_100a pipeline, download).
+  // pp_plan_batch_host_split (upload, the sm_100a pipeline, download).  The first PP_PREV_KEEP
+  // points of a trajectory are the frame's own previous points (result_points =
+  // prev_trajectory, src/main.cpp:578), so they are taken from the frame and only the new points
+  // cross PCIe: the heads are aliased onto the previous-point arrays.
   std::vector<Plan> plan(const std::vector<Frame> &frames) {
     const size_t n = frames.size();
     size_t mc = 1;
@@ -591,14 +594,13 @@ class Planner {
     in.car_vx = cvx.data();
     in.car_vy = cvy.data();
     in.max_cars = (int32_t)mc;
-    std::vector<double> nx(n * PP_PATH_LEN), ny(n * PP_PATH_LEN), d[8];
+    const size_t tail_len = PP_PATH_LEN - PP_PREV_KEEP;
+    std::vector<double> tx(n * tail_len), ty(n * tail_len), d[8];
     for (auto &v : d) v.resize(n);
     std::vector<int32_t> np(n), el(n), rw(n), otl(n), id0(n), id1(n);
     std::vector<uint32_t> fl(n);
     pp_plans out;
     std::memset(&out, 0, sizeof out);
-    out.next_x = nx.data();
-    out.next_y = ny.data();
     out.n_points = np.data();
     out.ego_lane = el.data();
     out.ref_wp = rw.data();
@@ -621,12 +623,21 @@ class Planner {
     out.car_vs = cvs.data();
     out.car_vd = cvd.data();
     out.car_lane = cl.data();
-    check(pp_plan_batch_host(map_.handle(), &cfg_, &in, &out, (int64_t)n), "pp_plan_batch_host");
+    pp_split_rows rows;
+    rows.head_x = px.data();  // on return: the first points of every trajectory
+    rows.head_y = py.data();
+    rows.tail_x = tx.data();
+    rows.tail_y = ty.data();
+    check(pp_plan_batch_host_split(map_.handle(), &cfg_, &in, &out, &rows, (int64_t)n),
+          "pp_plan_batch_host_split");
     std::vector<Plan> plans(n);
     for (size_t i = 0; i < n; i++) {
       Plan &p = plans[i];
-      p.next_x.assign(nx.begin() + i * PP_PATH_LEN, nx.begin() + i * PP_PATH_LEN + np[i]);
-      p.next_y.assign(ny.begin() + i * PP_PATH_LEN, ny.begin() + i * PP_PATH_LEN + np[i]);
+      const size_t cnt = (size_t)np[i], head = cnt < (size_t)PP_PREV_KEEP ? cnt : (size_t)PP_PREV_KEEP;
+      p.next_x.assign(px.begin() + i * PP_PREV_KEEP, px.begin() + i * PP_PREV_KEEP + head);
+      p.next_y.assign(py.begin() + i * PP_PREV_KEEP, py.begin() + i * PP_PREV_KEEP + head);
+      p.next_x.insert(p.next_x.end(), tx.begin() + i * tail_len, tx.begin() + i * tail_len + (cnt - head));
+      p.next_y.insert(p.next_y.end(), ty.begin() + i * tail_len, ty.begin() + i * tail_len + (cnt - head));
       p.target_lane = otl[i];
       p.ego_lane = el[i];
       p.ref_wp = rw[i];

@@ -83,6 +83,18 @@ def test_argument_validation(pp, pmap):
     assert rc in (-5, -2)  # PP_E_RANGE (or PP_E_CUDA first when there is no device)
     assert lib.pp_set_kernel_variant(7) == -1
     assert lib.pp_spline_batch(None, None, 5, None, 1, None, C.c_int64(1), None) == -1
+    # split rows: the four row arrays are required, whole rows may not be asked for as well
+    fs.max_cars = 12
+    z = np.zeros((4, 50))
+    rows = pp.abi.SplitRows(z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data)
+    args = (pmap.handle, C.byref(cfg), C.byref(fs), C.byref(ps))
+    assert lib.pp_plan_batch_host_split(*args, None, C.c_int64(4)) == -1
+    assert lib.pp_plan_batch_host_split(*args, C.byref(rows), C.c_int64(4)) == -1  # next_x set
+    ps.next_x = ps.next_y = None
+    rows.tail_y = None
+    assert lib.pp_plan_batch_host_split(*args, C.byref(rows), C.c_int64(4)) == -1
+    assert lib.pp_host_alloc(None, C.c_size_t(16)) == -1
+    assert lib.pp_host_free(None) == 0
 
 
 def test_no_cpu_fallback_without_gpu(pp, pmap):
@@ -94,6 +106,13 @@ def test_no_cpu_fallback_without_gpu(pp, pmap):
     fb = pp.synth_frames(pmap, 8, 12)
     with pytest.raises(pp.PPError, match="CUDA"):
         pp.plan_batch_host(pmap, fb)
+    sp = pp.PlanBatch(8, 12, diag=False, cars=False)
+    sp.next_x = sp.next_y = None
+    with pytest.raises(pp.PPError, match="CUDA"):
+        pp.plan_batch_host_split(pmap, fb, sp, fb.prev_x, fb.prev_y, np.zeros((8, 40)),
+                                 np.zeros((8, 40)))
+    with pytest.raises(pp.PPError, match="CUDA"):
+        pp.pinned_empty(16)
     assert pp.launch_count() == 0
 
 

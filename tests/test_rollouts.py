@@ -90,6 +90,7 @@ def test_rollout_groups_and_graph_replay_match_cpu_model(pp, oracle):
     m = pp.Map()
     a = pp.Rollouts(m, n, c, seed=seed)
     b = pp.Rollouts(m, n, c, seed=seed)
+    a.set_groups(3)  # three stream groups of 4,096; b: automatic (one group at this size)
     os.environ["PP_ROLLOUT_GRAPH"] = "1"
     try:
         a.run(ticks, k)        # >= 8 ticks: one direct tick, then graph replays
@@ -115,6 +116,31 @@ def test_rollout_groups_and_graph_replay_match_cpu_model(pp, oracle):
     now = a.state()
     for f in STATE_FIELDS:
         assert np.array_equal(getattr(now, f), getattr(cpu, f)), f
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [700, 6000])
+def test_rollout_statistics_are_the_sum_of_the_ticks(pp, n):
+    """pp_rollouts_stats == sum over the ticks of pp_stats_batch over that tick's plans, every
+    entry, the trajectory checksum included — for a job small enough for the single-kernel
+    planner (the simulator kernel takes the checksum) and for one on the pipeline (the planning
+    kernels add it as they write the points)."""
+    import torch
+    c, ticks, k = 12, 5, 2
+    m = pp.Map()
+    ro = pp.Rollouts(m, n, c, seed=5)
+    want = np.zeros(pp.STATS_LEN, dtype=np.int64)
+    for _ in range(ticks):
+        ro.run(1, k)
+        _, plans = ro.last()
+        dp = pp.DevicePlans(n, max(c, 1), diag=False, cars=False)
+        for name in dp.t:
+            a = getattr(plans, name)
+            dp.t[name].copy_(torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a))
+        want += pp.stats_batch(dp).cpu().numpy()
+    got = ro.stats().cpu().numpy()
+    assert np.array_equal(got, want), (got, want)
+    assert got[pp.abi.STAT_XSUM] != 0
 
 
 @pytest.mark.gpu
