@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -469,9 +470,10 @@ __global__ void __launch_bounds__(256) k_move_small(const Move p, int64_t n) {
   }
 }
 
-// the device's view of a page-locked host pointer, or null when the memory is pageable
-char *mapped_view(const void *host) {
-  if (!host) return nullptr;
+// the device's view of a page-locked host pointer, or null when the memory is pageable (or
+// the array is not aligned to its elements: such a caller gets the copy engine)
+char *mapped_view(const void *host, size_t elem) {
+  if (!host || ((uintptr_t)host & (elem - 1)) != 0) return nullptr;
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
     cudaGetLastError();
@@ -568,14 +570,15 @@ int plan_host(const pp_map *map, const pp_config *cfg, const pp_frames *in, cons
   static const bool zero_copy = getenv("PP_HOST_NO_ZERO_COPY") == nullptr;
   char *min_view[kIn] = {}, *mout_view[23] = {};
   if (zero_copy) {
-    for (int i : {0, 1, 2, 3, 4, 7, 8}) min_view[i] = mapped_view(hin[i].p);
-    for (int i = 2; i < 17; i++) mout_view[i] = mapped_view(hout[i].p);
+    for (int i : {0, 1, 2, 3, 4, 7, 8}) min_view[i] = mapped_view(hin[i].p, hin[i].bpf);
+    for (int i = 2; i < 17; i++) mout_view[i] = mapped_view(hout[i].p, hout[i].bpf);
   }
 
   // (Measured and dropped, profiles/bench_r2b_n1_{pitched,flat}_d2h.json: bringing down only the
   // 40 new columns of a trajectory with a pitched copy — the 10 kept ones are the caller's own
   // previous points — and filling the rest on the host moves 17 % fewer bytes but runs at
-  // 44.7 M frames/s against 52.3 M for whole rows: 320-byte rows are a poor DMA shape.)
+  // 44.7 M frames/s against 52.3 M for whole rows: 320-byte rows are a poor DMA shape.  The
+  // split-rows entry point compacts the new columns on the device instead.)
   // Nothing may still be writing into the caller's buffers when this returns, whatever the
   // outcome: a failure below joins the streams before it reports.
   struct Join {

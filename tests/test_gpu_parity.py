@@ -306,6 +306,12 @@ def test_host_entry_points_with_page_locked_buffers(pp, torch_cuda, gmap):
     pf = pp.FrameBatch(n, fb.max_cars)
     for k, v in fb.arrays().items():
         setattr(pf, k, pp.pinned_like(v))
+    # one page-locked array that is NOT aligned to its elements: it takes the copy engine
+    raw = pp.pinned_empty(n * 8 + 8, np.uint8)
+    odd = raw[4:4 + n * 8].view(np.float64)
+    odd[:] = fb.ego_y
+    assert odd.ctypes.data % 8 == 4
+    pf.ego_y = odd
     got = pp.PlanBatch(n, fb.max_cars)
     for k in got.fields:
         setattr(got, k, pp.pinned_like(getattr(got, k)))
