@@ -139,7 +139,7 @@ constexpr int kR = 32;  // rollouts per block (one warp's worth: the ego part is
 
 // frame <- state.  The block's threads sweep the rollouts' scalars (a warp per field), their
 // kept points and their car slots, all coalesced.
-__global__ void __launch_bounds__(kB)
+__global__ void __launch_bounds__(kB, 6)
 k_sim_frames(Track trk, int64_t lo, int64_t n, int c, SimState st, pp_plans pl, pp_frames fr) {
   const int64_t r0 = lo + (int64_t)blockIdx.x * kR;
   int64_t r_end = r0 + kR;
@@ -183,55 +183,110 @@ k_sim_frames(Track trk, int64_t lo, int64_t n, int c, SimState st, pp_plans pl, 
 static_assert(kB >= 7 * 32 && kR == 32, "k_sim_frames: a warp per scalar field, a lane per rollout");
 
 // state <- simulator step(plan), and this tick's contribution to the aggregate statistics
-// (definition: pp_stats_batch).  The car slots first (they read the rollout's tick before it is
-// counted), then one warp for the egos.  The trajectory checksum normally comes from the planning
-// kernels, which add it up as they write the points (plan_batch_scratch, xsum_add): re-reading
-// 800 bytes per rollout for it was two thirds of this kernel's traffic.  For the single-kernel
-// paths of small jobs the block takes it here, over its rollouts' rows (one contiguous run).
+// (definition: pp_stats_batch).  Warp 0 advances the egos, a lane per rollout, while the other
+// warps sweep the car slots: the two parts touch different state except for the rollout's tick
+// counter, which the respawn of a car reads, so only its increment waits behind the barrier
+// (with the ego part after the barrier the block's other seven warps sat in it for 59 % of the
+// kernel, profiles/r2_k_sim_advance_ncu.txt).  The counters are taken with warp votes, no
+// atomics in shared memory.  The trajectory checksum normally comes from the planning kernels,
+// which add it up as they write the points (plan_batch_scratch, xsum_add): re-reading 800 bytes
+// per rollout for it was two thirds of this kernel's traffic.  For the single-kernel paths of
+// small jobs the block takes it here, over its rollouts' rows (one contiguous run).
 __global__ void __launch_bounds__(kB)
 k_sim_advance(Track trk, int64_t lo, int64_t n, int c, uint64_t seed, int64_t first, int consume_k,
               SimState st, pp_plans pl, unsigned long long *stats_sum, int do_xsum) {
-  __shared__ unsigned long long s_acc[PP_STATS_LEN];
-  for (int i = threadIdx.x; i < PP_STATS_LEN; i += blockDim.x) s_acc[i] = 0;
   const int64_t r0 = lo + (int64_t)blockIdx.x * kR;
   int64_t r_end = r0 + kR;
   if (r_end > lo + n) r_end = lo + n;
   const int nr = (int)(r_end - r0);
-  // ---- traffic (one thread per car slot)
-  for (int64_t q = r0 * c + threadIdx.x; q < r_end * c; q += kB) {
-    const int64_t r = q / c;
-    const int j = (int)(q - r * c);
-    const int np = pl.n_points[r];
-    const int k = consume_k < np ? consume_k : np;
-    const double dt = kTick * (k > 0 ? k : 1);
-    int lane = st.car_lane[q], w = st.car_wp[q];
-    double u = st.car_ratio[q], v = st.car_speed[q];
-    const int m_lane = pl.car_lane[q];
-    const double m_s = pl.car_s[q];
-    if (m_lane < 0 || m_s < -100.0 || m_s > 300.0) {  // respawn
-      const int64_t tick = st.ticks[r];
-      const uint64_t key = mix64(mix64(seed ^ 0x5157ull) ^ ((uint64_t)(first + r) * 0xD1B54A32D192ED03ull));
-      const uint64_t h = mix64(key ^ ((uint64_t)tick * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)j << 48));
-      const double u1 = u01(mix64(h + 1)), u2 = u01(mix64(h + 2)), u3 = u01(mix64(h + 3));
-      const double ds = (m_lane >= 0 && m_s < -100.0) ? 200.0 + 100.0 * u1 : -(60.0 + 40.0 * u1);
-      lane = (int)(3.0 * u2);
-      if (lane > 2) lane = 2;
-      v = 17.88 + 8.94 * u3;
-      w = pl.ref_wp[r];
-      u = 0.5;
-      trk.walk(w, u, lane, ds);
-    } else {  // constant speed along the lane centre line
-      u += (v * dt) / trk.len(w, lane);
-      for (int guard = 0; guard < 64 && u >= 1; guard++) {
-        const double left = (u - 1) * trk.len(w, lane);
-        w = w + 1 == trk.n ? 0 : w + 1;
-        u = left / trk.len(w, lane);
+  if (threadIdx.x < 32) {
+    // ---- the ego consumes k points of the new trajectory (one lane per rollout)
+    const int ln = threadIdx.x;
+    const bool live = ln < nr;
+    const int64_t r = r0 + (live ? ln : 0);
+    const int np = live ? pl.n_points[r] : 0;
+    int tl = -1, el = -1;
+    uint32_t fl = 0;
+    if (live) {
+      const int k = consume_k < np ? consume_k : np;
+      if (k > 0) {
+        const double ox = st.ego_x[r], oy = st.ego_y[r];
+        const double qx = pl.next_x[r * PP_PATH_LEN + k - 1], qy = pl.next_y[r * PP_PATH_LEN + k - 1];
+        const double d = sqrt((qx - ox) * (qx - ox) + (qy - oy) * (qy - oy));
+        st.ego_x[r] = qx;
+        st.ego_y[r] = qy;
+        st.ego_mph[r] = d / (kTick * k) * 2.237;
       }
+      st.path_n[r] = np - k;
+      st.path_off[r] = k;
+      tl = pl.target_lane[r];
+      el = pl.ego_lane[r];
+      st.target_lane[r] = tl;
+      fl = pl.flags[r];
     }
-    st.car_lane[q] = lane;
-    st.car_wp[q] = w;
-    st.car_ratio[q] = u;
-    st.car_speed[q] = v;
+    // counters: lane i ends up holding entry i of the statistics vector
+    const unsigned full = 0xffffffffu;
+    unsigned long long mine = 0;
+    unsigned long long pts = (unsigned long long)np;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pts += __shfl_xor_sync(full, pts, o);
+    const unsigned n_live = __popc(__ballot_sync(full, live));
+    if (ln == PP_STAT_FRAMES) mine = n_live;
+    if (ln == PP_STAT_POINTS) mine = pts;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const unsigned a = __popc(__ballot_sync(full, live && tl == q));
+      const unsigned b = __popc(__ballot_sync(full, live && el == q));
+      if (ln == PP_STAT_TARGET_LANE0 + q) mine = a;
+      if (ln == PP_STAT_EGO_LANE0 + q) mine = b;
+    }
+    {
+      const unsigned a = __popc(__ballot_sync(full, live && tl != el));
+      if (ln == PP_STAT_LANE_CHANGES) mine = a;
+    }
+#pragma unroll
+    for (int b = 0; b < PP_NUM_FLAGS; b++) {
+      const unsigned a = __popc(__ballot_sync(full, (fl >> b) & 1u));
+      if (ln == PP_STAT_FLAG0 + b) mine = a;
+    }
+    if (ln < PP_STATS_LEN && ln != PP_STAT_XSUM && mine) atomicAdd(&stats_sum[ln], mine);
+  } else {
+    // ---- traffic (one thread per car slot; they read the rollout's tick before it is counted)
+    for (int64_t q = r0 * c + (threadIdx.x - 32); q < r_end * c; q += kB - 32) {
+      const int64_t r = q / c;
+      const int j = (int)(q - r * c);
+      const int np = pl.n_points[r];
+      const int k = consume_k < np ? consume_k : np;
+      const double dt = kTick * (k > 0 ? k : 1);
+      int lane = st.car_lane[q], w = st.car_wp[q];
+      double u = st.car_ratio[q], v = st.car_speed[q];
+      const int m_lane = pl.car_lane[q];
+      const double m_s = pl.car_s[q];
+      if (m_lane < 0 || m_s < -100.0 || m_s > 300.0) {  // respawn
+        const int64_t tick = st.ticks[r];
+        const uint64_t key = mix64(mix64(seed ^ 0x5157ull) ^ ((uint64_t)(first + r) * 0xD1B54A32D192ED03ull));
+        const uint64_t h = mix64(key ^ ((uint64_t)tick * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)j << 48));
+        const double u1 = u01(mix64(h + 1)), u2 = u01(mix64(h + 2)), u3 = u01(mix64(h + 3));
+        const double ds = (m_lane >= 0 && m_s < -100.0) ? 200.0 + 100.0 * u1 : -(60.0 + 40.0 * u1);
+        lane = (int)(3.0 * u2);
+        if (lane > 2) lane = 2;
+        v = 17.88 + 8.94 * u3;
+        w = pl.ref_wp[r];
+        u = 0.5;
+        trk.walk(w, u, lane, ds);
+      } else {  // constant speed along the lane centre line
+        u += (v * dt) / trk.len(w, lane);
+        for (int guard = 0; guard < 64 && u >= 1; guard++) {
+          const double left = (u - 1) * trk.len(w, lane);
+          w = w + 1 == trk.n ? 0 : w + 1;
+          u = left / trk.len(w, lane);
+        }
+      }
+      st.car_lane[q] = lane;
+      st.car_wp[q] = w;
+      st.car_ratio[q] = u;
+      st.car_speed[q] = v;
+    }
   }
   if (do_xsum) {  // ---- checksum of the block's rows, unless the planning kernels added it
     long long xs = 0;
@@ -246,40 +301,12 @@ k_sim_advance(Track trk, int64_t lo, int64_t n, int c, uint64_t seed, int64_t fi
     unsigned long long v = (unsigned long long)xs;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_acc[PP_STAT_XSUM], v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&stats_sum[PP_STAT_XSUM], v);
   }
   __syncthreads();
-  // ---- the ego consumes k points of the new trajectory (one lane per rollout, one warp)
-  if (threadIdx.x < nr) {
-    const int64_t r = r0 + threadIdx.x;
-    const int np = pl.n_points[r];
-    const int k = consume_k < np ? consume_k : np;
-    if (k > 0) {
-      const double ox = st.ego_x[r], oy = st.ego_y[r];
-      const double qx = pl.next_x[r * PP_PATH_LEN + k - 1], qy = pl.next_y[r * PP_PATH_LEN + k - 1];
-      const double d = sqrt((qx - ox) * (qx - ox) + (qy - oy) * (qy - oy));
-      st.ego_x[r] = qx;
-      st.ego_y[r] = qy;
-      st.ego_mph[r] = d / (kTick * k) * 2.237;
-    }
-    st.path_n[r] = np - k;
-    st.path_off[r] = k;
-    const int tl = pl.target_lane[r], el = pl.ego_lane[r];
-    st.target_lane[r] = tl;
-    st.ticks[r] += 1;
-    const uint32_t fl = pl.flags[r];
-    atomicAdd(&s_acc[PP_STAT_FRAMES], 1ull);
-    atomicAdd(&s_acc[PP_STAT_POINTS], (unsigned long long)np);
-    if (tl >= 0 && tl < 3) atomicAdd(&s_acc[PP_STAT_TARGET_LANE0 + tl], 1ull);
-    if (el >= 0 && el < 3) atomicAdd(&s_acc[PP_STAT_EGO_LANE0 + el], 1ull);
-    if (tl != el) atomicAdd(&s_acc[PP_STAT_LANE_CHANGES], 1ull);
-    for (int b = 0; b < PP_NUM_FLAGS; b++)
-      if (fl & (1u << b)) atomicAdd(&s_acc[PP_STAT_FLAG0 + b], 1ull);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < PP_STATS_LEN; i += blockDim.x)
-    if (s_acc[i]) atomicAdd(&stats_sum[i], s_acc[i]);
+  if (threadIdx.x < nr) st.ticks[r0 + threadIdx.x] += 1;
 }
+static_assert(PP_STATS_LEN <= 32, "k_sim_advance: a lane per statistics entry");
 
 inline size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
 
